@@ -1,0 +1,51 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace dots {
+
+typedef __nv_bfloat16 bf16;
+
+// Error plumbing: every C-ABI entry returns 0 or a negative code; text via dots_last_error().
+void set_error(const char* fmt, ...);
+int num_sms();
+
+#define DOTS_CHECK_CUDA(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            dots::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return -2;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+#define DOTS_REQUIRE(cond, ...)                                                            \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            dots::set_error(__VA_ARGS__);                                                  \
+            return -1;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+#define DOTS_LAUNCH_CHECK()                                                                \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            dots::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return -3;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+// 2-D bf16 row-major tensor [rows, cols] with row pitch ld (elements) -> TMA map with a
+// {64 x box_rows} box and 128-byte swizzle.  Returns 0 on success.
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols = 64);
+// 3-D variant: [d2, d1, d0] with strides (elements) s2, s1, unit inner stride.
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                      uint64_t s2, uint32_t b0, uint32_t b1, uint32_t b2);
+
+}  // namespace dots

@@ -1,0 +1,665 @@
+// HBM-bound kernels of the dots.ocr hot path: casts, RMSNorm / LayerNorm, 2-D and 1-D RoPE,
+// KV-cache append, token embedding + image scatter, greedy argmax, and the decode-step
+// "finalize" kernels that fold split-K reduction, bias, residual, norm, RoPE and cache append
+// into one pass each.  All are coalesced 16-byte-vector kernels with warp-shuffle reductions;
+// rounding points follow the HF eager path (fp32 inside a norm / rope / softmax, one bf16 rounding
+// where HF materialises a bf16 tensor).
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/dots_ocr_b200.h"
+
+namespace dots {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------ cast + pad
+// pixel_values [rows, cols] (fp32 or bf16) -> bf16 [rows, ldo], columns >= cols zero-filled
+// (TMA needs a 16-byte row pitch; 588 * 2 B is not).  HF: hidden_states.to(bf16).
+__global__ void cast_pad_kernel(const void* __restrict__ in, int in_is_bf16, long long rows, int cols, bf16* __restrict__ out,
+                                int ldo) {
+    const long long total = rows * (ldo / 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (ldo / 2);
+        const int c = (int)(i % (ldo / 2)) * 2;
+        float a = 0.f, b = 0.f;
+        if (in_is_bf16) {
+            const bf16* src = reinterpret_cast<const bf16*>(in) + r * cols;
+            if (c < cols) a = __bfloat162float(src[c]);
+            if (c + 1 < cols) b = __bfloat162float(src[c + 1]);
+        } else {
+            const float* src = reinterpret_cast<const float*>(in) + r * cols;
+            if (c < cols) a = src[c];
+            if (c + 1 < cols) b = src[c + 1];
+        }
+        *reinterpret_cast<uint32_t*>(out + r * ldo + c) = pack_bf16x2(a, b);
+    }
+}
+
+// ------------------------------------------------------------------ RMSNorm (one warp per row)
+// out = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )        (Qwen2RMSNorm, modeling_qwen2.py:258-263)
+constexpr int NORM_MAX_CHUNKS = 8;     // per lane; cols <= 8 * 32 * 8 = 2048 on the register path
+
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
+                                                      bf16* __restrict__ out, long long ldo, long long rows, int cols, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * 8LL + warp;
+    if (row >= rows) return;
+    const int nchunks = cols >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(x + row * ldx);
+    uint4 v[NORM_MAX_CHUNKS];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            v[i] = src[c];
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+        }
+    }
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss / (float)cols + eps);
+    const uint4* wsrc = reinterpret_cast<const uint4*>(w);
+    uint4* dst = reinterpret_cast<uint4*>(out + row * ldo);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            float f[8], g[8];
+            unpack8(v[i], f);
+            unpack8(__ldg(wsrc + c), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] * r) * g[j];
+            dst[c] = pack8(f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm (PatchMerger.ln_q)
+// fp32 statistics, out = bf16((x - mean) * rstd * w + b)       (torch.nn.LayerNorm, eps 1e-6)
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
+                                                        const bf16* __restrict__ b, bf16* __restrict__ out, long long ldo,
+                                                        long long rows, int cols, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * 8LL + warp;
+    if (row >= rows) return;
+    const int nchunks = cols >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(x + row * ldx);
+    uint4 v[NORM_MAX_CHUNKS];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            v[i] = src[c];
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[j];
+        }
+    }
+    const float mean = warp_sum(s) / (float)cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; sq += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+    const uint4* wsrc = reinterpret_cast<const uint4*>(w);
+    const uint4* bsrc = reinterpret_cast<const uint4*>(b);
+    uint4* dst = reinterpret_cast<uint4*>(out + row * ldo);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            float f[8], g[8], h[8];
+            unpack8(v[i], f);
+            unpack8(__ldg(wsrc + c), g);
+            unpack8(__ldg(bsrc + c), h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * g[j] + h[j];
+            dst[c] = pack8(f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ViT 2-D RoPE
+// cos/sin table [S, 64] fp32: angle[s, j] = (j < 32 ? h(s) : w(s)) * inv_freq[j % 32]
+// token order = processor order: 2x2 merge blocks contiguous (dots_ocr.py:536-568).
+__global__ void vit_rope_table_kernel(const int* __restrict__ cu, const int* __restrict__ grid_hw, int n_img,
+                                      const float* __restrict__ inv_freq, int half, int merge, float* __restrict__ cos_t,
+                                      float* __restrict__ sin_t, int total_tokens) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dim = 2 * half;
+    if (idx >= total_tokens * dim) return;
+    const int s = idx / dim, j = idx % dim;
+    int img = 0;
+    while (img + 1 < n_img && s >= cu[img + 1]) ++img;
+    const int n = s - cu[img];
+    const int W = grid_hw[2 * img + 1];
+    const int per_frame = grid_hw[2 * img] * W;
+    const int nn = n % per_frame;
+    const int blk = nn / (merge * merge), in = nn % (merge * merge);
+    const int bw = W / merge;
+    const int hpos = (blk / bw) * merge + in / merge;
+    const int wpos = (blk % bw) * merge + in % merge;
+    const float ang = __fmul_rn((float)(j < half ? hpos : wpos), inv_freq[j % half]);
+    cos_t[idx] = cosf(ang);
+    sin_t[idx] = sinf(ang);
+}
+
+// In-place NeoX rotate-half on the q and k thirds of a fused qkv buffer [S, 3 * heads * 128], fp32 math,
+// one rounding (ApplyRotaryEmb, enable_fp32_compute=True).  One thread = 8 (x1, x2) pairs.
+__global__ void vit_rope_apply_kernel(bf16* __restrict__ qkv, long long ld, int S, int heads, const float* __restrict__ cos_t,
+                                      const float* __restrict__ sin_t) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = (long long)S * heads * 2 * 8;
+    if (idx >= total) return;
+    const int c8 = (int)(idx & 7);
+    const int hh = (int)((idx >> 3) % (heads * 2));
+    const long long s = idx / (8LL * heads * 2);
+    bf16* base = qkv + s * ld + (long long)hh * 128 + c8 * 8;     // q heads then k heads are contiguous
+    uint4 u1 = *reinterpret_cast<uint4*>(base), u2 = *reinterpret_cast<uint4*>(base + 64);
+    float x1[8], x2[8], o1[8], o2[8];
+    unpack8(u1, x1);
+    unpack8(u2, x2);
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + s * 64 + c8 * 8);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + s * 64 + c8 * 8);
+    float c[8], sn[8];
+    *reinterpret_cast<float4*>(c) = cp[0]; *reinterpret_cast<float4*>(c + 4) = cp[1];
+    *reinterpret_cast<float4*>(sn) = sp[0]; *reinterpret_cast<float4*>(sn + 4) = sp[1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        o1[j] = __fsub_rn(__fmul_rn(x1[j], c[j]), __fmul_rn(x2[j], sn[j]));
+        o2[j] = __fadd_rn(__fmul_rn(x2[j], c[j]), __fmul_rn(x1[j], sn[j]));
+    }
+    *reinterpret_cast<uint4*>(base) = pack8(o1);
+    *reinterpret_cast<uint4*>(base + 64) = pack8(o2);
+}
+
+// ------------------------------------------------------------------ LLM 1-D RoPE (+ KV append)
+// HF Qwen2: cos/sin are bf16 tensors; q_embed = q * cos + rotate_half(q) * sin evaluated in bf16
+// (every product and the sum round to bf16)   (modeling_qwen2.py:102-146).
+__device__ __forceinline__ void rope_bf16_8(const float (&x1)[8], const float (&x2)[8], int pos, const float* inv_freq, int i0,
+                                            float (&o1)[8], float (&o2)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float ang = __fmul_rn((float)pos, inv_freq[i0 + j]);
+        const float c = bf16_round(cosf(ang)), s = bf16_round(sinf(ang));
+        o1[j] = bf16_round(__fadd_rn(bf16_round(__fmul_rn(x1[j], c)), bf16_round(__fmul_rn(-x2[j], s))));
+        o2[j] = bf16_round(__fadd_rn(bf16_round(__fmul_rn(x2[j], c)), bf16_round(__fmul_rn(x1[j], s))));
+    }
+}
+
+// Prefill: qkv [T, (nq + 2 nkv) * 128] (bias already added by the GEMM epilogue).  Rotates q and k
+// in place (the prefill attention reads them from this buffer) and appends k, v to the cache.
+__global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int T, int nq, int nkv, const int* __restrict__ pos,
+                                       const int* __restrict__ seq_of_tok, const float* __restrict__ inv_freq,
+                                       bf16* __restrict__ kc, bf16* __restrict__ vc, long long ctx_max) {
+    const int units = (nq + 2 * nkv) * 8;           // 8 threads per head (each: 8 low + 8 high dims)
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * units) return;
+    const int tkn = (int)(idx / units);
+    const int u = (int)(idx % units);
+    const int head = u >> 3, c8 = u & 7;
+    bf16* base = qkv + (long long)tkn * ld + head * 128 + c8 * 8;
+    const int p = pos[tkn];
+    if (head < nq + nkv) {
+        float x1[8], x2[8], o1[8], o2[8];
+        unpack8(*reinterpret_cast<uint4*>(base), x1);
+        unpack8(*reinterpret_cast<uint4*>(base + 64), x2);
+        rope_bf16_8(x1, x2, p, inv_freq, c8 * 8, o1, o2);
+        const uint4 r1 = pack8(o1), r2 = pack8(o2);
+        *reinterpret_cast<uint4*>(base) = r1;
+        *reinterpret_cast<uint4*>(base + 64) = r2;
+        if (head >= nq) {
+            bf16* dst = kc + (((long long)seq_of_tok[tkn] * nkv + (head - nq)) * ctx_max + p) * 128 + c8 * 8;
+            *reinterpret_cast<uint4*>(dst) = r1;
+            *reinterpret_cast<uint4*>(dst + 64) = r2;
+        }
+    } else {
+        bf16* dst = vc + (((long long)seq_of_tok[tkn] * nkv + (head - nq - nkv)) * ctx_max + p) * 128 + c8 * 8;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(base);
+        *reinterpret_cast<uint4*>(dst + 64) = *reinterpret_cast<uint4*>(base + 64);
+    }
+}
+
+// ------------------------------------------------------------------ embedding + image scatter
+// slots[t] = rank of token t among image-pad tokens (masked_scatter order), or -1 for text tokens.
+__global__ void __launch_bounds__(1024) image_slots_kernel(const long long* __restrict__ ids, int T, long long image_token,
+                                                           int* __restrict__ slots, int* __restrict__ count_out) {
+    __shared__ int warp_excl[32];
+    __shared__ int chunk_total;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < T; base += 1024) {
+        const int tkn = base + threadIdx.x;
+        const int flag = (tkn < T && ids[tkn] == image_token) ? 1 : 0;
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_excl[warp] = incl;          // per-warp totals
+        __syncthreads();
+        if (warp == 0) {
+            const int wv = warp_excl[lane];
+            int wi = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_excl[lane] = wi - wv;                   // exclusive prefix over warps
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (tkn < T) slots[tkn] = flag ? (carry + warp_excl[warp] + incl - flag) : -1;
+        __syncthreads();                                 // everyone has read carry
+        if (threadIdx.x == 0) carry += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && count_out) *count_out = carry;
+}
+
+__global__ void embed_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ slots, const bf16* __restrict__ table,
+                                     const bf16* __restrict__ img, bf16* __restrict__ out, int T, int H, long long vocab) {
+    const int chunks = H >> 3;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * chunks) return;
+    const int tkn = (int)(idx / chunks), c = (int)(idx % chunks);
+    const int slot = slots ? slots[tkn] : -1;
+    const bf16* src;
+    if (slot >= 0) src = img + (long long)slot * H;
+    else {
+        long long id = ids[tkn];
+        if (id < 0 || id >= vocab) id = 0;
+        src = table + id * H;
+    }
+    reinterpret_cast<uint4*>(out + (long long)tkn * H)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+}
+
+__global__ void gather_rows_kernel(const bf16* __restrict__ src, long long lds, const int* __restrict__ rows, bf16* __restrict__ out,
+                                   long long ldo, int n, int cols) {
+    const int chunks = cols >> 3;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * chunks) return;
+    const int r = (int)(idx / chunks), c = (int)(idx % chunks);
+    reinterpret_cast<uint4*>(out + (long long)r * ldo)[c] = reinterpret_cast<const uint4*>(src + (long long)rows[r] * lds)[c];
+}
+
+// ------------------------------------------------------------------ greedy argmax + sequence state advance
+// logits bf16 -> fp32 -> argmax, lowest index wins ties (torch.argmax; generation/utils.py:2762,2793).
+// Then the HF bookkeeping of one greedy step: finished rows emit pad, EOS marks a row finished
+// (utils.py:2796-2805), the token is appended, position / context length advance.
+__global__ void __launch_bounds__(1024) argmax_advance_kernel(const bf16* __restrict__ logits, long long ldl, int V,
+                                                              long long* __restrict__ next_ids, long long* __restrict__ out_ids,
+                                                              long long out_ld, int* __restrict__ step, int* __restrict__ pos,
+                                                              int* __restrict__ ctx_len, int* __restrict__ finished,
+                                                              long long eos_id, long long pad_id, const long long* __restrict__ forced,
+                                                              long long forced_ld) {
+    const int b = blockIdx.x;
+    const bf16* row = logits + (long long)b * ldl;
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    const int nchunks = V >> 3;
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(row) + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (f[j] > best) { best = f[j]; bidx = c * 8 + j; }       // strictly greater: first index kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    __shared__ float sb[32];
+    __shared__ int si[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sb[warp] = best; si[warp] = bidx; }
+    __syncthreads();
+    if (warp == 0) {
+        best = (lane < (blockDim.x >> 5)) ? sb[lane] : -INFINITY;
+        bidx = (lane < (blockDim.x >> 5)) ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (lane == 0) {
+            long long tok = bidx;
+            const int st = step ? step[b] : 0;
+            if (forced) tok = forced[(long long)b * forced_ld + st];   // teacher forcing (parity tests)
+            if (finished) {
+                if (finished[b]) tok = pad_id;
+                else if (eos_id >= 0 && tok == eos_id) finished[b] = 1;
+            }
+            next_ids[b] = tok;
+            if (out_ids) out_ids[(long long)b * out_ld + st] = tok;
+            if (step) step[b] = st + 1;
+            if (pos) pos[b] += 1;
+            if (ctx_len) ctx_len[b] += 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ decode-step finalize kernels
+// All take split-K partial sums [splits][B][N] fp32 from dots_gemm_skinny_bf16 and reduce them in a
+// fixed order (deterministic), then apply the HF rounding points.
+
+// x = embed[last_id]; resid = x; normed = RMSNorm(x) * w          (one warp per sequence)
+__global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table,
+                                                                   long long vocab, const bf16* __restrict__ w, bf16* __restrict__ resid,
+                                                                   bf16* __restrict__ normed, int B, int H, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    long long id = ids[b];
+    if (id < 0 || id >= vocab) id = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(table + id * H);
+    const int nchunks = H >> 3;
+    uint4 v[NORM_MAX_CHUNKS];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            v[i] = __ldg(src + c);
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+            reinterpret_cast<uint4*>(resid + (long long)b * H)[c] = v[i];
+        }
+    }
+    const float r = rsqrtf(warp_sum(ss) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            float f[8], g[8];
+            unpack8(v[i], f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] * r) * g[j];
+            reinterpret_cast<uint4*>(normed + (long long)b * H)[c] = pack8(f);
+        }
+    }
+}
+
+// x = bf16(sum partial); resid = bf16(resid + x); normed = RMSNorm(resid) * w      (one warp per sequence)
+__global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const float* __restrict__ partial, int splits,
+                                                                      bf16* __restrict__ resid, const bf16* __restrict__ w,
+                                                                      bf16* __restrict__ normed, int B, int H, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    const int nchunks = H >> 3;
+    float vals[NORM_MAX_CHUNKS][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int s = 0; s < splits; ++s) {
+                const float4* ps = reinterpret_cast<const float4*>(partial + ((long long)s * B + b) * H + c * 8);
+                const float4 a = ps[0], d = ps[1];
+                acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                acc[4] += d.x; acc[5] += d.y; acc[6] += d.z; acc[7] += d.w;
+            }
+            float rr[8];
+            unpack8(reinterpret_cast<const uint4*>(resid + (long long)b * H)[c], rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x = bf16_round(bf16_round(acc[j]) + rr[j]);
+                vals[i][j] = x;
+                ss += x * x;
+            }
+            reinterpret_cast<uint4*>(resid + (long long)b * H)[c] = pack8(vals[i]);
+        }
+    }
+    const float r = rsqrtf(warp_sum(ss) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            float g[8], f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = bf16_round(vals[i][j] * r) * g[j];
+            reinterpret_cast<uint4*>(normed + (long long)b * H)[c] = pack8(f);
+        }
+    }
+}
+
+// q,k,v = bf16(sum partial + bias); RoPE(q, k) at pos[b]; q -> q_out, k,v -> cache[b, :, pos[b]]
+__global__ void decode_qkv_rope_append_kernel(const float* __restrict__ partial, int splits, const bf16* __restrict__ bias,
+                                              const int* __restrict__ pos, const float* __restrict__ inv_freq, bf16* __restrict__ q_out,
+                                              bf16* __restrict__ kc, bf16* __restrict__ vc, long long ctx_max, int B, int nq, int nkv) {
+    const int units = (nq + 2 * nkv) * 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * units) return;
+    const int b = idx / units, u = idx % units;
+    const int head = u >> 3, c8 = u & 7;
+    const int N = (nq + 2 * nkv) * 128;
+    const int col = head * 128 + c8 * 8;
+    float x1[8], x2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x1[j] = 0.f; x2[j] = 0.f; }
+    for (int s = 0; s < splits; ++s) {
+        const float* ps = partial + ((long long)s * B + b) * N + col;
+        const float4 a = *reinterpret_cast<const float4*>(ps), d = *reinterpret_cast<const float4*>(ps + 4);
+        const float4 e = *reinterpret_cast<const float4*>(ps + 64), f = *reinterpret_cast<const float4*>(ps + 68);
+        x1[0] += a.x; x1[1] += a.y; x1[2] += a.z; x1[3] += a.w; x1[4] += d.x; x1[5] += d.y; x1[6] += d.z; x1[7] += d.w;
+        x2[0] += e.x; x2[1] += e.y; x2[2] += e.z; x2[3] += e.w; x2[4] += f.x; x2[5] += f.y; x2[6] += f.z; x2[7] += f.w;
+    }
+    float b1[8], b2[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(bias + col)), b1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(bias + col + 64)), b2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x1[j] = bf16_round(x1[j] + b1[j]); x2[j] = bf16_round(x2[j] + b2[j]); }
+    const int p = pos[b];
+    if (head < nq + nkv) {
+        float o1[8], o2[8];
+        rope_bf16_8(x1, x2, p, inv_freq, c8 * 8, o1, o2);
+        bf16* dst = (head < nq) ? q_out + ((long long)b * nq + head) * 128 + c8 * 8
+                                : kc + (((long long)b * nkv + (head - nq)) * ctx_max + p) * 128 + c8 * 8;
+        *reinterpret_cast<uint4*>(dst) = pack8(o1);
+        *reinterpret_cast<uint4*>(dst + 64) = pack8(o2);
+    } else {
+        bf16* dst = vc + (((long long)b * nkv + (head - nq - nkv)) * ctx_max + p) * 128 + c8 * 8;
+        *reinterpret_cast<uint4*>(dst) = pack8(x1);
+        *reinterpret_cast<uint4*>(dst + 64) = pack8(x2);
+    }
+}
+
+// act = bf16( bf16(silu(bf16 gate)) * bf16 up ), gate/up interleaved per 256-column block
+// ([128 gate | 128 up], the layout the prefill SWIGLU epilogue uses), partial [splits][B][2I].
+__global__ void decode_swiglu_kernel(const float* __restrict__ partial, int splits, bf16* __restrict__ act, int B, int I) {
+    const int chunks = I >> 3;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * chunks) return;
+    const int b = idx / chunks, c = idx % chunks;
+    const int col = c * 8;
+    const int gcol = (col >> 7) * 256 + (col & 127);
+    float gsum[8], usum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gsum[j] = 0.f; usum[j] = 0.f; }
+    for (int s = 0; s < splits; ++s) {
+        const float* ps = partial + ((long long)s * B + b) * (2LL * I) + gcol;
+        const float4 a = *reinterpret_cast<const float4*>(ps), d = *reinterpret_cast<const float4*>(ps + 4);
+        const float4 e = *reinterpret_cast<const float4*>(ps + 128), f = *reinterpret_cast<const float4*>(ps + 132);
+        gsum[0] += a.x; gsum[1] += a.y; gsum[2] += a.z; gsum[3] += a.w; gsum[4] += d.x; gsum[5] += d.y; gsum[6] += d.z; gsum[7] += d.w;
+        usum[0] += e.x; usum[1] += e.y; usum[2] += e.z; usum[3] += e.w; usum[4] += f.x; usum[5] += f.y; usum[6] += f.z; usum[7] += f.w;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float gv = bf16_round(gsum[j]), uv = bf16_round(usum[j]);
+        o[j] = bf16_round(gv / (1.0f + expf(-gv))) * uv;
+    }
+    reinterpret_cast<uint4*>(act + (long long)b * I)[c] = pack8(o);
+}
+
+}  // namespace dots
+
+using namespace dots;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int dots_cast_pad_bf16(const void* in, int in_is_bf16, long long rows, int cols, void* out, int ldo, void* stream) {
+    DOTS_REQUIRE(rows > 0 && cols > 0 && ldo >= cols && ldo % 8 == 0, "dots_cast_pad_bf16: bad shape rows=%lld cols=%d ldo=%d", rows, cols, ldo);
+    const long long total = rows * (ldo / 2);
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    cast_pad_kernel<<<blocks, 256, 0, ST(stream)>>>(in, in_is_bf16, rows, cols, (bf16*)out, ldo);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, long long rows, int cols,
+                            float eps, void* stream) {
+    DOTS_REQUIRE(rows > 0 && cols % 8 == 0 && cols <= NORM_MAX_CHUNKS * 256 && ldx % 8 == 0 && ldo % 8 == 0,
+                 "dots_rmsnorm: need cols %% 8 == 0, cols <= 2048, 16-byte pitches (cols=%d)", cols);
+    rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)out, ldo, rows, cols, eps);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_layernorm(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo,
+                              long long rows, int cols, float eps, void* stream) {
+    DOTS_REQUIRE(rows > 0 && cols % 8 == 0 && cols <= NORM_MAX_CHUNKS * 256 && ldx % 8 == 0 && ldo % 8 == 0,
+                 "dots_layernorm: need cols %% 8 == 0, cols <= 2048, 16-byte pitches (cols=%d)", cols);
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)out, ldo,
+                                                                       rows, cols, eps);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_vit_rope_table(const int* cu_seqlens, const int* grid_hw, int n_img, const float* inv_freq, int half,
+                                   int merge, float* cos_t, float* sin_t, int total_tokens, void* stream) {
+    DOTS_REQUIRE(n_img > 0 && total_tokens > 0 && half == 32 && merge > 0, "dots_vit_rope_table: bad args (half must be 32)");
+    const long long n = (long long)total_tokens * 2 * half;
+    vit_rope_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(cu_seqlens, grid_hw, n_img, inv_freq, half, merge, cos_t, sin_t,
+                                                                             total_tokens);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_vit_rope_apply(void* qkv, long long ld, int S, int heads, int head_dim, const float* cos_t, const float* sin_t,
+                                   void* stream) {
+    DOTS_REQUIRE(S > 0 && heads > 0 && head_dim == 128 && ld % 8 == 0, "dots_vit_rope_apply: head_dim must be 128, pitch %% 8 == 0");
+    const long long n = (long long)S * heads * 2 * 8;
+    vit_rope_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((bf16*)qkv, ld, S, heads, cos_t, sin_t);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_llm_rope_kv_append(void* qkv, long long ld, int T, int n_q_heads, int n_kv_heads, int head_dim,
+                                       const int* positions, const int* seq_of_tok, const float* inv_freq, void* k_cache,
+                                       void* v_cache, long long ctx_max, void* stream) {
+    DOTS_REQUIRE(T > 0 && head_dim == 128 && ld % 8 == 0, "dots_llm_rope_kv_append: head_dim must be 128");
+    const long long n = (long long)T * (n_q_heads + 2 * n_kv_heads) * 8;
+    llm_rope_append_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((bf16*)qkv, ld, T, n_q_heads, n_kv_heads, positions,
+                                                                              seq_of_tok, inv_freq, (bf16*)k_cache, (bf16*)v_cache, ctx_max);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_image_slots(const long long* ids, int T, long long image_token_id, int* slots, int* count_out, void* stream) {
+    DOTS_REQUIRE(T > 0, "dots_image_slots: empty input");
+    image_slots_kernel<<<1, 1024, 0, ST(stream)>>>(ids, T, image_token_id, slots, count_out);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_embed_scatter(const long long* ids, const int* slots, const void* table, const void* img_embeds, void* out,
+                                  int T, int H, long long vocab, void* stream) {
+    DOTS_REQUIRE(T > 0 && H % 8 == 0, "dots_embed_scatter: bad shape");
+    const long long n = (long long)T * (H / 8);
+    embed_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(ids, slots, (const bf16*)table, (const bf16*)img_embeds, (bf16*)out,
+                                                                            T, H, vocab);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_gather_rows(const void* src, long long lds, const int* rows, void* out, long long ldo, int n, int cols,
+                                void* stream) {
+    DOTS_REQUIRE(n > 0 && cols % 8 == 0 && lds % 8 == 0 && ldo % 8 == 0, "dots_gather_rows: bad shape");
+    const long long t = (long long)n * (cols / 8);
+    gather_rows_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>((const bf16*)src, lds, rows, (bf16*)out, ldo, n, cols);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_argmax_advance(const void* logits, long long ldl, int batch, int vocab, long long* next_ids, long long* out_ids,
+                                   long long out_ld, int* step, int* pos, int* ctx_len, int* finished, long long eos_id,
+                                   long long pad_id, const long long* forced_ids, long long forced_ld, void* stream) {
+    DOTS_REQUIRE(batch > 0 && vocab % 8 == 0 && ldl % 8 == 0, "dots_argmax_advance: vocab and pitch must be multiples of 8");
+    argmax_advance_kernel<<<batch, 1024, 0, ST(stream)>>>((const bf16*)logits, ldl, vocab, next_ids, out_ids, out_ld, step, pos, ctx_len,
+                                                         finished, eos_id, pad_id, forced_ids, forced_ld);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
+                                         void* normed, int batch, int H, float eps, void* stream) {
+    DOTS_REQUIRE(batch > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_embed_rmsnorm: H %% 8, H <= 2048");
+    decode_embed_rmsnorm_kernel<<<(batch + 7) / 8, 256, 0, ST(stream)>>>(ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid,
+                                                                        (bf16*)normed, batch, H, eps);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed, int batch,
+                                            int H, float eps, void* stream) {
+    DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
+    decode_residual_rmsnorm_kernel<<<(batch + 7) / 8, 256, 0, ST(stream)>>>(partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch,
+                                                                           H, eps);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_decode_qkv_rope_append(const float* partial, int splits, const void* bias, const int* pos, const float* inv_freq,
+                                           void* q_out, void* k_cache, void* v_cache, long long ctx_max, int batch, int n_q_heads,
+                                           int n_kv_heads, int head_dim, void* stream) {
+    DOTS_REQUIRE(batch > 0 && splits > 0 && head_dim == 128, "dots_decode_qkv_rope_append: head_dim must be 128");
+    const int n = batch * (n_q_heads + 2 * n_kv_heads) * 8;
+    decode_qkv_rope_append_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(partial, splits, (const bf16*)bias, pos, inv_freq, (bf16*)q_out,
+                                                                          (bf16*)k_cache, (bf16*)v_cache, ctx_max, batch, n_q_heads, n_kv_heads);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_decode_swiglu(const float* partial, int splits, void* act, int batch, int inter, void* stream) {
+    DOTS_REQUIRE(batch > 0 && splits > 0 && inter % 128 == 0, "dots_decode_swiglu: intermediate size must be a multiple of 128");
+    const int n = batch * (inter / 8);
+    decode_swiglu_kernel<<<(n + 255) / 256, 256, 0, ST(stream)>>>(partial, splits, (bf16*)act, batch, inter);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,432 @@
+// bf16 GEMM on the 5th-gen tensor cores:  D[M,N] = A[M,K] * B[N,K]^T  (both operands K-major).
+//
+//   TMA (cp.async.bulk.tensor, 128-B swizzle) -> shared-memory ring -> tcgen05.mma (one elected
+//   thread) -> fp32 accumulators in TMEM (double buffered) -> tcgen05.ld -> fused epilogue -> HBM.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (one TMEM lane quarter each).  One CTA per SM.
+//
+// Used for every dense contraction on the dots.ocr hot path (SURVEY.md §8a rows a5, a8, a11-a13,
+// a16, a20-a22).  Epilogues reproduce the HF eager rounding points (each nn.Linear rounds to bf16
+// before the next elementwise op).
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/dots_ocr_b200.h"
+
+namespace dots {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;        // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int ACC_STAGES = 2;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+    int M, N, K;                   // rows of A, rows of B, reduction length
+    int m_blocks, n_blocks, splits, kb_per_split, num_k_blocks;
+    void* out;
+    long long ldo;
+    const bf16* bias;
+    const bf16* res;
+    long long ldr;
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
+                                   : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_blk, int& n_blk, int& split) {
+    split = t % p.splits;
+    int r = t / p.splits;
+    n_blk = r % p.n_blocks;
+    m_blk = r / p.n_blocks;
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+    using S = GemmSmem<BLOCK_N>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;         // [ACC_STAGES]
+    uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < ACC_STAGES; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);            // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr, S::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk, split;
+                tile_coords(p, t, m_blk, n_blk, split);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
+                    tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk, split;
+                tile_coords(p, t, m_blk, n_blk, split);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * S::A_BYTES));
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * S::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the >>4 address field
+                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int wq = warp & 3;                             // TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int m_blk, n_blk, split;
+            tile_coords(p, t, m_blk, n_blk, split);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + wq * 32 + lane;          // row of A this thread owns
+            const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
+
+            if constexpr (EPI == DOTS_EPI_SWIGLU) {
+                // B rows are interleaved per 256-block: [128 gate rows | 128 up rows]; out has N/2 columns.
+                static_assert(EPI != DOTS_EPI_SWIGLU || BLOCK_N == 256, "swiglu epilogue needs BLOCK_N=256");
+                bf16* out = reinterpret_cast<bf16*>(p.out);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, g);
+                    tmem_ld_32x32b_x32(t_row + 128 + c * 32, u);
+                    tmem_ld_wait();
+                    const int col = n_blk * 128 + c * 32;
+                    if (row < p.M) {
+                        uint32_t o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float g0 = bf16_round(__uint_as_float(g[2 * j])), g1 = bf16_round(__uint_as_float(g[2 * j + 1]));
+                            float u0 = bf16_round(__uint_as_float(u[2 * j])), u1 = bf16_round(__uint_as_float(u[2 * j + 1]));
+                            float a0 = bf16_round(silu_f(g0)), a1 = bf16_round(silu_f(g1));
+                            o[j] = pack_bf16x2(a0 * u0, a1 * u1);
+                        }
+                        bf16* dst = out + (long long)row * p.ldo + col;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (col + q * 8 + 8 <= p.N / 2)
+                                *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    }
+                }
+            } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
+                // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
+                // partial[split][b][feature] fp32; lanes write consecutive features (coalesced).
+                float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int b = n_blk * BLOCK_N + c * 32 + j;
+                            if (b < p.N) out[((long long)split * p.N + b) * p.ldo + row] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            } else if constexpr (EPI == DOTS_EPI_BF16_T) {
+                // swap-AB, no split: out[b][feature] = bf16(acc + bias[feature]); lanes = consecutive features.
+                bf16* out = reinterpret_cast<bf16*>(p.out);
+                const float bias_v = (p.bias != nullptr && row < p.M) ? __bfloat162float(p.bias[row]) : 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int b = n_blk * BLOCK_N + c * 32 + j;
+                            if (b < p.N) out[(long long)b * p.ldo + row] = __float2bfloat16_rn(__uint_as_float(v[j]) + bias_v);
+                        }
+                    }
+                }
+            } else {
+                bf16* out = reinterpret_cast<bf16*>(p.out);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const int col = n_blk * BLOCK_N + c * 32;
+                    if (row < p.M && col < p.N) {
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if constexpr (EPI == DOTS_EPI_BIAS || EPI == DOTS_EPI_BIAS_GELU) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (col + q * 8 + 8 <= p.N) {
+                                    uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col + q * 8));
+                                    f[q * 8 + 0] += bf16_lo(b.x); f[q * 8 + 1] += bf16_hi(b.x);
+                                    f[q * 8 + 2] += bf16_lo(b.y); f[q * 8 + 3] += bf16_hi(b.y);
+                                    f[q * 8 + 4] += bf16_lo(b.z); f[q * 8 + 5] += bf16_hi(b.z);
+                                    f[q * 8 + 6] += bf16_lo(b.w); f[q * 8 + 7] += bf16_hi(b.w);
+                                }
+                            }
+                        }
+                        if constexpr (EPI == DOTS_EPI_BIAS_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(bf16_round(f[j]));
+                        }
+                        if constexpr (EPI == DOTS_EPI_RESIDUAL) {
+                            const bf16* rsrc = p.res + (long long)row * p.ldr + col;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (col + q * 8 + 8 <= p.N) {
+                                    uint4 r = *reinterpret_cast<const uint4*>(rsrc + q * 8);
+                                    f[q * 8 + 0] = bf16_round(f[q * 8 + 0]) + bf16_lo(r.x);
+                                    f[q * 8 + 1] = bf16_round(f[q * 8 + 1]) + bf16_hi(r.x);
+                                    f[q * 8 + 2] = bf16_round(f[q * 8 + 2]) + bf16_lo(r.y);
+                                    f[q * 8 + 3] = bf16_round(f[q * 8 + 3]) + bf16_hi(r.y);
+                                    f[q * 8 + 4] = bf16_round(f[q * 8 + 4]) + bf16_lo(r.z);
+                                    f[q * 8 + 5] = bf16_round(f[q * 8 + 5]) + bf16_hi(r.z);
+                                    f[q * 8 + 6] = bf16_round(f[q * 8 + 6]) + bf16_lo(r.w);
+                                    f[q * 8 + 7] = bf16_round(f[q * 8 + 7]) + bf16_hi(r.w);
+                                }
+                            }
+                        }
+                        bf16* dst = out + (long long)row * p.ldo + col;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (col + q * 8 + 8 <= p.N) {
+                                uint4 o;
+                                o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                                o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                                o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                                o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                                *reinterpret_cast<uint4*>(dst + q * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            // release this accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    using S = GemmSmem<BLOCK_N>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    const int tiles = p.m_blocks * p.n_blocks * p.splits;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, p);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dots
+
+using namespace dots;
+
+extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                              int M, int N, int K, int epilogue, const void* bias, const void* residual,
+                              long long ldr, void* stream) {
+    DOTS_REQUIRE(M > 0 && N > 0 && K > 0, "dots_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    DOTS_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && N % 8 == 0,
+                 "dots_gemm_bf16: K, N and all pitches must be multiples of 8 (16-byte TMA/vector alignment)");
+    DOTS_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+                 "dots_gemm_bf16: pointers must be 16-byte aligned");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.out = out; p.ldo = ldo;
+    p.bias = reinterpret_cast<const bf16*>(bias);
+    p.res = reinterpret_cast<const bf16*>(residual);
+    p.ldr = ldr;
+    p.splits = 1;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb_per_split = p.num_k_blocks;
+    p.m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta, tb;
+    if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M)) return -4;
+
+    if (epilogue == DOTS_EPI_SWIGLU) {
+        DOTS_REQUIRE(N % 256 == 0, "dots_gemm_bf16: SWIGLU epilogue needs N %% 256 == 0 (got %d)", N);
+        p.n_blocks = N / 256;
+        if (make_tmap_2d_bf16(&tb, W, N, K, ldw, 256)) return -4;
+        return launch_gemm<256, DOTS_EPI_SWIGLU>(ta, tb, p, st);
+    }
+    if ((epilogue == DOTS_EPI_BIAS || epilogue == DOTS_EPI_BIAS_GELU) && !bias) {
+        set_error("dots_gemm_bf16: bias epilogue without bias pointer");
+        return -1;
+    }
+    if (epilogue == DOTS_EPI_RESIDUAL) {
+        DOTS_REQUIRE(residual && ldr % 8 == 0, "dots_gemm_bf16: residual epilogue needs residual pointer, ldr %% 8 == 0");
+    }
+    // Tile width: 256 when it divides the work well, else 128 (more tiles for small problems).
+    const long long tiles256 = (long long)p.m_blocks * ((N + 255) / 256);
+    const bool use256 = (N % 256 == 0 || N > 4096) && tiles256 >= 2LL * num_sms();
+    if (use256) {
+        p.n_blocks = (N + 255) / 256;
+        if (make_tmap_2d_bf16(&tb, W, N, K, ldw, 256)) return -4;
+        switch (epilogue) {
+            case DOTS_EPI_STORE: return launch_gemm<256, DOTS_EPI_STORE>(ta, tb, p, st);
+            case DOTS_EPI_BIAS: return launch_gemm<256, DOTS_EPI_BIAS>(ta, tb, p, st);
+            case DOTS_EPI_BIAS_GELU: return launch_gemm<256, DOTS_EPI_BIAS_GELU>(ta, tb, p, st);
+            case DOTS_EPI_RESIDUAL: return launch_gemm<256, DOTS_EPI_RESIDUAL>(ta, tb, p, st);
+        }
+    } else {
+        p.n_blocks = (N + 127) / 128;
+        if (make_tmap_2d_bf16(&tb, W, N, K, ldw, 128)) return -4;
+        switch (epilogue) {
+            case DOTS_EPI_STORE: return launch_gemm<128, DOTS_EPI_STORE>(ta, tb, p, st);
+            case DOTS_EPI_BIAS: return launch_gemm<128, DOTS_EPI_BIAS>(ta, tb, p, st);
+            case DOTS_EPI_BIAS_GELU: return launch_gemm<128, DOTS_EPI_BIAS_GELU>(ta, tb, p, st);
+            case DOTS_EPI_RESIDUAL: return launch_gemm<128, DOTS_EPI_RESIDUAL>(ta, tb, p, st);
+        }
+    }
+    set_error("dots_gemm_bf16: unknown epilogue %d", epilogue);
+    return -1;
+}
+
+// Decode-time (skinny) GEMM, swap-AB + split-K:  partial[s][b][n] = sum_{k in split s} X[b,k] * W[n,k].
+// The weight matrix is the 128-row tcgen05 M operand so that a batch of <= 256 rows still runs on
+// the tensor cores while the weights stream once from HBM.
+extern "C" int dots_gemm_skinny_bf16(const void* X, long long ldx, const void* W, long long ldw, float* partial,
+                                     void* out_bf16, long long ldo, const void* bias, int batch, int N, int K, int splits,
+                                     void* stream) {
+    DOTS_REQUIRE(batch > 0 && batch <= 256 && N > 0 && K > 0, "dots_gemm_skinny_bf16: bad shape batch=%d N=%d K=%d", batch, N, K);
+    DOTS_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "dots_gemm_skinny_bf16: K and pitches must be multiples of 8");
+    DOTS_REQUIRE((partial != nullptr) != (out_bf16 != nullptr), "dots_gemm_skinny_bf16: pass exactly one of partial / out_bf16");
+    GemmParams p{};
+    p.M = N;               // A operand = weights: rows are output features
+    p.N = batch;           // B operand = activations
+    p.K = K;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    if (splits < 1) splits = 1;
+    if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+    p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+    p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // every split non-empty
+    DOTS_REQUIRE(p.splits == splits, "dots_gemm_skinny_bf16: splits=%d does not tile %d k-blocks (would use %d)", splits,
+                 p.num_k_blocks, p.splits);
+    const bool to_bf16 = out_bf16 != nullptr;
+    if (to_bf16) {
+        DOTS_REQUIRE(splits == 1, "dots_gemm_skinny_bf16: bf16 output needs splits == 1");
+        p.out = out_bf16; p.ldo = ldo; p.bias = reinterpret_cast<const bf16*>(bias);
+    } else {
+        p.out = partial; p.ldo = N;
+    }
+    p.m_blocks = (N + BLOCK_M - 1) / BLOCK_M;
+    p.n_blocks = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta, tb;
+    if (make_tmap_2d_bf16(&ta, W, N, K, ldw, BLOCK_M)) return -4;
+    const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
+    if (make_tmap_2d_bf16(&tb, X, batch, K, ldx, bn)) return -4;
+    if (to_bf16) {
+        switch (bn) {
+            case 32: return launch_gemm<32, DOTS_EPI_BF16_T>(ta, tb, p, st);
+            case 64: return launch_gemm<64, DOTS_EPI_BF16_T>(ta, tb, p, st);
+            case 128: return launch_gemm<128, DOTS_EPI_BF16_T>(ta, tb, p, st);
+            default: return launch_gemm<256, DOTS_EPI_BF16_T>(ta, tb, p, st);
+        }
+    }
+    switch (bn) {
+        case 32: return launch_gemm<32, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
+        case 64: return launch_gemm<64, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
+        case 128: return launch_gemm<128, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
+        default: return launch_gemm<256, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
+    }
+}

@@ -1,0 +1,354 @@
+"""In-process engine for the dots.ocr page-parsing hot path on one B200.
+
+Replaces what ``self.model.generate(**inputs, max_new_tokens=N)`` does in the reference
+(``dots_ocr/parser.py:110``): DotsVisionTransformer forward -> embed + masked_scatter ->
+Qwen2 prefill -> greedy decode with a KV cache.  Host code is Python; every device operation
+is a call into libdots_ocr_b200.so (``ops``).  torch is used for tensor storage, streams and a
+handful of index-array constructions on the host side.
+
+Layout in HBM (all bf16 unless noted):
+  * weights: nn.Linear layout [out, in]; fused qkv; gate|up (fc1|fc3) interleaved per 256 rows
+    as [128 gate | 128 up] so the SwiGLU epilogue finds both halves in one accumulator tile.
+  * activations: token-major packed [sum_tokens, width] (no padding between sequences).
+  * KV cache: [layers, batch, kv_heads, ctx_max, 128], appended in place.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .config import DotsConfig
+
+
+def _interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    I, H = gate.shape
+    assert I % 128 == 0, "intermediate size must be a multiple of 128"
+    g = gate.view(I // 128, 128, H)
+    u = up.view(I // 128, 128, H)
+    return torch.stack([g, u], dim=1).reshape(2 * I, H).contiguous()
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class GenerateOutput:
+    sequences: torch.Tensor                 # [B, T + N] int64 (prompt included, HF layout)
+    logits: Optional[torch.Tensor] = None   # [B, N, V] bf16 pre-sampling logits (when requested)
+    image_embeds: Optional[torch.Tensor] = None
+
+
+class Engine:
+    def __init__(self, cfg: DotsConfig, ckpt: Dict[str, torch.Tensor], device: str | torch.device = "cuda:0"):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("dots_ocr_b200.Engine needs a CUDA device (there is no CPU fallback)")
+        from . import _lib
+        _lib.load()
+        torch.cuda.set_device(self.device)
+        v, t = cfg.vision, cfg.text
+        assert v.head_dim == 128 and t.head_dim == 128, "kernels are specialised for head_dim 128"
+        dev = self.device
+
+        def W(name):
+            return ckpt[name].to(device=dev, dtype=torch.bfloat16).contiguous()
+
+        # ---- vision tower ---------------------------------------------------------------
+        self.patch_k = _round_up(v.patch_dim, 64)                   # 588 -> 640 (TMA row pitch % 16 B)
+        pw = W("vision_tower.patch_embed.patchifier.proj.weight").reshape(v.embed_dim, v.patch_dim)
+        self.v_patch_w = torch.zeros((v.embed_dim, self.patch_k), device=dev, dtype=torch.bfloat16)
+        self.v_patch_w[:, : v.patch_dim] = pw
+        self.v_patch_b = W("vision_tower.patch_embed.patchifier.proj.bias")
+        self.v_patch_norm = W("vision_tower.patch_embed.patchifier.norm.weight")
+        self.v_layers: List[dict] = []
+        for i in range(v.num_hidden_layers):
+            p = f"vision_tower.blocks.{i}."
+            self.v_layers.append(dict(
+                norm1=W(p + "norm1.weight"), qkv=W(p + "attn.qkv.weight"), proj=W(p + "attn.proj.weight"),
+                norm2=W(p + "norm2.weight"),
+                fc13=_interleave_gate_up(W(p + "mlp.fc1.weight"), W(p + "mlp.fc3.weight")),
+                fc2=W(p + "mlp.fc2.weight")))
+        self.v_post_norm = W("vision_tower.post_trunk_norm.weight")
+        self.v_ln_w = W("vision_tower.merger.ln_q.weight")
+        self.v_ln_b = W("vision_tower.merger.ln_q.bias")
+        self.v_m0_w = W("vision_tower.merger.mlp.0.weight")
+        self.v_m0_b = W("vision_tower.merger.mlp.0.bias")
+        self.v_m2_w = W("vision_tower.merger.mlp.2.weight")
+        self.v_m2_b = W("vision_tower.merger.mlp.2.bias")
+        half = v.head_dim // 4                                      # 32 frequencies per axis
+        dim = v.head_dim // 2
+        self.v_inv_freq = (1.0 / (v.rope_theta ** (torch.arange(0, dim, 2, dtype=torch.float) / dim))).to(dev)
+        assert self.v_inv_freq.numel() == half
+
+        # ---- decoder --------------------------------------------------------------------
+        self.embed = W("model.embed_tokens.weight")
+        self.t_layers: List[dict] = []
+        for i in range(t.num_hidden_layers):
+            p = f"model.layers.{i}."
+            qkv_w = torch.cat([W(p + "self_attn.q_proj.weight"), W(p + "self_attn.k_proj.weight"),
+                               W(p + "self_attn.v_proj.weight")], dim=0).contiguous()
+            qkv_b = torch.cat([W(p + "self_attn.q_proj.bias"), W(p + "self_attn.k_proj.bias"),
+                               W(p + "self_attn.v_proj.bias")], dim=0).contiguous()
+            self.t_layers.append(dict(
+                ln1=W(p + "input_layernorm.weight"), qkv_w=qkv_w, qkv_b=qkv_b, o=W(p + "self_attn.o_proj.weight"),
+                ln2=W(p + "post_attention_layernorm.weight"),
+                gu=_interleave_gate_up(W(p + "mlp.gate_proj.weight"), W(p + "mlp.up_proj.weight")),
+                down=W(p + "mlp.down_proj.weight")))
+        self.final_norm = W("model.norm.weight")
+        self.lm_head = W("lm_head.weight")
+        hd = t.head_dim
+        self.t_inv_freq = (1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
+        self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.launches = 0       # C-ABI kernel launches issued (bench.py reports it)
+
+    # ------------------------------------------------------------------------------ vision
+    @torch.no_grad()
+    def encode_images(self, pixel_values: torch.Tensor, image_grid_thw, return_layers: bool = False):
+        """DotsVisionTransformer.forward ([V] dots_ocr.py:580-611): pixel_values [sum S, 588] ->
+        image embeddings [sum S / 4, hidden]."""
+        v = self.cfg.vision
+        dev = self.device
+        grid = image_grid_thw.tolist() if torch.is_tensor(image_grid_thw) else [list(g) for g in image_grid_thw]
+        seqlens, ghw = [], []
+        for tt, h, w in grid:
+            for _ in range(int(tt)):
+                seqlens.append(int(h) * int(w))
+                ghw.append([int(h), int(w)])
+        S = sum(seqlens)
+        pv = pixel_values.to(dev)
+        assert pv.shape == (S, v.patch_dim), (pv.shape, S, v.patch_dim)
+        cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+        ghw_t = torch.tensor(ghw, dtype=torch.int32, device=dev)
+        max_seqlen = max(seqlens)
+        D, Hh = v.embed_dim, v.num_attention_heads
+        scale = v.head_dim ** -0.5
+
+        cos, sin = ops.vit_rope_table(cu, ghw_t, self.v_inv_freq, v.spatial_merge_size, S)
+        xin = ops.cast_pad(pv.contiguous(), self.patch_k)
+        x = ops.gemm(xin, self.v_patch_w, epilogue=ops.EPI_BIAS, bias=self.v_patch_b)
+        del xin
+        x = ops.rmsnorm(x, self.v_patch_norm, v.rms_norm_eps, out=x)
+        self.launches += 4
+        normed = torch.empty_like(x)
+        qkv = torch.empty((S, 3 * D), device=dev, dtype=torch.bfloat16)
+        attn = torch.empty((S, D), device=dev, dtype=torch.bfloat16)
+        act = torch.empty((S, v.intermediate_size), device=dev, dtype=torch.bfloat16)
+        layers = [x.clone()] if return_layers else None
+        for L in self.v_layers:
+            ops.rmsnorm(x, L["norm1"], v.rms_norm_eps, out=normed)
+            ops.gemm(normed, L["qkv"], out=qkv)
+            ops.vit_rope_apply(qkv, Hh, cos, sin)
+            ops.attn_varlen(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], attn, cu, max_seqlen, Hh, Hh, False, scale)
+            ops.gemm(attn, L["proj"], out=x, epilogue=ops.EPI_RESIDUAL, residual=x)
+            ops.rmsnorm(x, L["norm2"], v.rms_norm_eps, out=normed)
+            ops.gemm(normed, L["fc13"], out=act, epilogue=ops.EPI_SWIGLU)
+            ops.gemm(act, L["fc2"], out=x, epilogue=ops.EPI_RESIDUAL, residual=x)
+            self.launches += 8
+            if return_layers:
+                layers.append(x.clone())
+        del qkv, attn, act
+        ops.rmsnorm(x, self.v_post_norm, v.rms_norm_eps, out=normed)
+        ops.layernorm(normed, self.v_ln_w, self.v_ln_b, v.merger_ln_eps, out=x)
+        merged = x.view(S // (v.spatial_merge_size ** 2), v.merge_dim)
+        h = ops.gemm(merged, self.v_m0_w, epilogue=ops.EPI_BIAS_GELU, bias=self.v_m0_b)
+        out = ops.gemm(h, self.v_m2_w, epilogue=ops.EPI_BIAS, bias=self.v_m2_b)
+        self.launches += 4
+        return (out, layers) if return_layers else out
+
+    # ------------------------------------------------------------------------------ decoder
+    def _alloc_cache(self, B: int, ctx_max: int):
+        t = self.cfg.text
+        shape = (t.num_hidden_layers, B, t.num_key_value_heads, ctx_max, t.head_dim)
+        k = torch.empty(shape, device=self.device, dtype=torch.bfloat16)
+        vv = torch.empty(shape, device=self.device, dtype=torch.bfloat16)
+        return k, vv
+
+    @torch.no_grad()
+    def _prefill(self, ids_packed, slots, img_embeds, cu, seq_lens, positions, seq_of_tok, kc, vc, ctx_max, want_hidden=False):
+        t = self.cfg.text
+        dev = self.device
+        T = ids_packed.numel()
+        nq, nkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
+        scale = hd ** -0.5
+        x = ops.embed_scatter(ids_packed, slots, self.embed, img_embeds)
+        normed = torch.empty_like(x)
+        qkv = torch.empty((T, (nq + 2 * nkv) * hd), device=dev, dtype=torch.bfloat16)
+        attn = torch.empty((T, nq * hd), device=dev, dtype=torch.bfloat16)
+        act = torch.empty((T, t.intermediate_size), device=dev, dtype=torch.bfloat16)
+        max_len = int(max(seq_lens))
+        self.launches += 1
+        for li, L in enumerate(self.t_layers):
+            ops.rmsnorm(x, L["ln1"], t.rms_norm_eps, out=normed)
+            ops.gemm(normed, L["qkv_w"], out=qkv, epilogue=ops.EPI_BIAS, bias=L["qkv_b"])
+            ops.llm_rope_kv_append(qkv, nq, nkv, positions, seq_of_tok, self.t_inv_freq, kc[li], vc[li], ctx_max)
+            ops.attn_varlen(qkv[:, : nq * hd], qkv[:, nq * hd:(nq + nkv) * hd], qkv[:, (nq + nkv) * hd:], attn, cu, max_len,
+                            nq, nkv, True, scale)
+            ops.gemm(attn, L["o"], out=x, epilogue=ops.EPI_RESIDUAL, residual=x)
+            ops.rmsnorm(x, L["ln2"], t.rms_norm_eps, out=normed)
+            ops.gemm(normed, L["gu"], out=act, epilogue=ops.EPI_SWIGLU)
+            ops.gemm(act, L["down"], out=x, epilogue=ops.EPI_RESIDUAL, residual=x)
+            self.launches += 8
+        return x
+
+    def _decode_plan(self, B: int):
+        t = self.cfg.text
+        H, I = t.hidden_size, t.intermediate_size
+        qkv_n = (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim
+        kb = lambda k: -(-k // 64)
+        tiles = lambda n: -(-n // 128)
+        return dict(
+            qkv=ops.pick_splits(tiles(qkv_n), kb(H), self.sms),
+            o=ops.pick_splits(tiles(H), kb(t.num_attention_heads * t.head_dim), self.sms),
+            gu=ops.pick_splits(tiles(2 * I), kb(H), self.sms),
+            down=ops.pick_splits(tiles(H), kb(I), self.sms),
+            attn=max(1, min(16, (3 * self.sms) // max(1, B * t.num_key_value_heads))),
+        )
+
+    def _decode_step(self, st: dict):
+        """One greedy step for the whole batch; every call is a C-ABI kernel launch (graph-capturable)."""
+        t = self.cfg.text
+        nq, nkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
+        pl = st["plan"]
+        scale = hd ** -0.5
+        ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
+        n_layers = len(self.t_layers)
+        for li, L in enumerate(self.t_layers):
+            ops.gemm_skinny(st["normed"], L["qkv_w"], pl["qkv"], partial=st["partial"])
+            ops.decode_qkv_rope_append(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["q"], st["kc"][li],
+                                       st["vc"][li], st["ctx_max"], nq, nkv)
+            ops.attn_decode(st["q"], st["kc"][li], st["vc"][li], st["ctx_len"], st["attn"], nq, nkv, st["ctx_max"], pl["attn"],
+                            scale, st["part_o"], st["part_ml"])
+            ops.gemm_skinny(st["attn"], L["o"], pl["o"], partial=st["partial"])
+            ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed"], t.rms_norm_eps)
+            ops.gemm_skinny(st["normed"], L["gu"], pl["gu"], partial=st["partial"])
+            ops.decode_swiglu(st["partial"], pl["gu"], st["act"])
+            ops.gemm_skinny(st["act"], L["down"], pl["down"], partial=st["partial"])
+            nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
+            ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed"], t.rms_norm_eps)
+        ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
+        ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
+                           st["eos"], st["pad"], st["forced"])
+
+    def launches_per_decode_step(self, B: int) -> int:
+        pl = self._decode_plan(B)
+        per_layer = 9 + (1 if pl["attn"] > 1 else 0)
+        return 1 + per_layer * len(self.t_layers) + 2
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                 pixel_values: Optional[torch.Tensor] = None, image_grid_thw=None, max_new_tokens: int = 16,
+                 eos_token_id: Optional[int] = None, pad_token_id: int = 0, forced_ids: Optional[torch.Tensor] = None,
+                 return_logits: bool = False, use_graph: bool = True, image_embeds: Optional[torch.Tensor] = None,
+                 **unused) -> GenerateOutput:
+        """HF-shaped greedy generation: returns ids [B, T + N'] including the prompt (parser.py:110-113)."""
+        t = self.cfg.text
+        dev = self.device
+        ids = input_ids.to(dev).long()
+        B, Tpad = ids.shape
+        assert B <= 256, "batch > 256 pages per call is not supported; shard the pages"
+        mask = torch.ones_like(ids) if attention_mask is None else attention_mask.to(dev).long()
+        lens = mask.sum(dim=1).to(torch.int64)
+        seq_lens = lens.tolist()
+        N = int(max_new_tokens)
+        assert N >= 1
+        ctx_max = _round_up(int(max(seq_lens)) + N, 64)
+
+        # packed (un-padded) token stream; HF positions = cumsum(mask) - 1
+        keep = mask.bool()
+        ids_packed = ids[keep].contiguous()
+        positions = (mask.cumsum(1) - 1)[keep].to(torch.int32).contiguous()
+        seq_of_tok = torch.arange(B, device=dev, dtype=torch.int32).unsqueeze(1).expand(B, Tpad)[keep].contiguous()
+        cu = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        cu[1:] = lens.cumsum(0).to(torch.int32)
+
+        if image_embeds is None and pixel_values is not None:
+            image_embeds = self.encode_images(pixel_values, image_grid_thw)
+        slots = None
+        if image_embeds is not None:
+            slots, count = ops.image_slots(ids_packed, self.cfg.image_token_id)
+            self.launches += 1
+            n_img = int(count.item())
+            if n_img != image_embeds.shape[0]:
+                raise ValueError(f"image tokens in input_ids ({n_img}) != image embedding rows ({image_embeds.shape[0]})")
+
+        kc, vc = self._alloc_cache(B, ctx_max)
+        x = self._prefill(ids_packed, slots, image_embeds, cu, seq_lens, positions, seq_of_tok, kc, vc, ctx_max)
+
+        H = t.hidden_size
+        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, eos=-1 if eos_token_id is None else int(eos_token_id),
+                  pad=int(pad_token_id))
+        pl = st["plan"]
+        max_part = max(pl["qkv"] * (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim, pl["o"] * H,
+                       pl["gu"] * 2 * t.intermediate_size, pl["down"] * H)
+        st["partial"] = torch.empty(max_part * B, device=dev, dtype=torch.float32)
+        st["resid"] = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
+        st["normed"] = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
+        st["q"] = torch.empty((B, t.num_attention_heads * t.head_dim), device=dev, dtype=torch.bfloat16)
+        st["attn"] = torch.empty_like(st["q"])
+        st["act"] = torch.empty((B, t.intermediate_size), device=dev, dtype=torch.bfloat16)
+        st["logits"] = torch.empty((B, t.vocab_size), device=dev, dtype=torch.bfloat16)
+        st["part_o"] = torch.empty((B, t.num_attention_heads, pl["attn"], t.head_dim), device=dev, dtype=torch.float32)
+        st["part_ml"] = torch.empty((B, t.num_attention_heads, pl["attn"], 2), device=dev, dtype=torch.float32)
+        st["last"] = torch.zeros(B, device=dev, dtype=torch.int64)
+        st["out_ids"] = torch.full((B, N), int(pad_token_id), device=dev, dtype=torch.int64)
+        st["step"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st["pos"] = (lens - 1).to(torch.int32)
+        st["ctx_len"] = lens.to(torch.int32)
+        st["finished"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st["forced"] = forced_ids.to(dev).long().contiguous() if forced_ids is not None else None
+        all_logits = torch.empty((N, B, t.vocab_size), device=dev, dtype=torch.bfloat16) if return_logits else None
+
+        # first token: final norm + lm_head on each sequence's last prompt position
+        last_rows = (cu[1:] - 1).to(torch.int32)
+        hl = ops.gather_rows(x, last_rows)
+        ops.rmsnorm(hl, self.final_norm, t.rms_norm_eps, out=st["normed"])
+        ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
+        ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
+                           st["eos"], st["pad"], st["forced"])
+        self.launches += 4
+        del x
+        if return_logits:
+            all_logits[0].copy_(st["logits"])
+
+        n_steps = N - 1
+        per_step = self.launches_per_decode_step(B)
+        if n_steps > 0:
+            if use_graph and not return_logits:
+                self._decode_step(st)                   # eager once (also warms every kernel variant)
+                done = 1
+                if n_steps > 1:
+                    g = ops.Graph()
+                    cap = torch.cuda.Stream(device=dev)
+                    cap.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(cap):
+                        with g:
+                            self._decode_step(st)
+                        # capture does not execute: replay for every remaining step
+                        for _ in range(n_steps - 1):
+                            g.launch()
+                    torch.cuda.current_stream().wait_stream(cap)
+                    done = n_steps
+                self.launches += per_step * done
+                st["_graph"] = None
+            else:
+                for s in range(n_steps):
+                    self._decode_step(st)
+                    if return_logits:
+                        all_logits[s + 1].copy_(st["logits"])
+                self.launches += per_step * n_steps
+
+        out_new = st["out_ids"]
+        if eos_token_id is not None:
+            fin_step = (out_new == int(eos_token_id)).int().argmax(dim=1)
+            has = (out_new == int(eos_token_id)).any(dim=1)
+            if bool(has.all()):
+                out_new = out_new[:, : int(fin_step.max().item()) + 1]      # HF stops once every row has finished
+        seqs = torch.cat([ids, out_new], dim=1)
+        return GenerateOutput(sequences=seqs, logits=all_logits.transpose(0, 1) if return_logits else None,
+                              image_embeds=image_embeds)

@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch tensors are containers only: each function
+checks dtype / device / alignment, then passes raw device pointers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+K = _lib.header_constants()
+EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_SWIGLU = (
+    K["DOTS_EPI_STORE"], K["DOTS_EPI_BIAS"], K["DOTS_EPI_BIAS_GELU"], K["DOTS_EPI_RESIDUAL"], K["DOTS_EPI_SWIGLU"])
+
+_ll = C.c_longlong
+_vp = C.c_void_p
+
+
+def _stream() -> _vp:
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> _vp:
+    return _vp(0 if t is None else t.data_ptr())
+
+
+def _bf16_2d(t: torch.Tensor, name: str) -> None:
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError(f"{name}: need a CUDA bf16 2-D tensor with unit inner stride, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, epilogue: int = EPI_STORE,
+         bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T); a [M, K], w [N, K] (nn.Linear layout)."""
+    _bf16_2d(a, "a"); _bf16_2d(w, "w")
+    M, Kd = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == Kd, (a.shape, w.shape)
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.bfloat16)
+    _bf16_2d(out, "out")
+    assert out.shape == (M, n_out), (out.shape, M, n_out)
+    ldr = residual.stride(0) if residual is not None else 0
+    rc = _lib.load().dots_gemm_bf16(_p(a), _ll(a.stride(0)), _p(w), _ll(w.stride(0)), _p(out), _ll(out.stride(0)),
+                                    M, N, Kd, epilogue, _p(bias), _p(residual), _ll(ldr), _stream())
+    _lib.check(rc, "dots_gemm_bf16")
+    return out
+
+
+def gemm_skinny(x: torch.Tensor, w: torch.Tensor, splits: int = 1, partial: Optional[torch.Tensor] = None,
+                out_bf16: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
+    """Decode GEMM (batch <= 256).  Returns fp32 partials [splits, B, N] or bf16 [B, N] when out_bf16 is given."""
+    _bf16_2d(x, "x"); _bf16_2d(w, "w")
+    B, Kd = x.shape
+    N = w.shape[0]
+    if out_bf16 is None and partial is None:
+        partial = torch.empty((splits, B, N), device=x.device, dtype=torch.float32)
+    if partial is not None:
+        assert partial.dtype == torch.float32 and partial.is_contiguous() and partial.numel() >= splits * B * N
+    ldo = out_bf16.stride(0) if out_bf16 is not None else 0
+    rc = _lib.load().dots_gemm_skinny_bf16(_p(x), _ll(x.stride(0)), _p(w), _ll(w.stride(0)),
+                                           _p(partial if out_bf16 is None else None), _p(out_bf16), _ll(ldo), _p(bias),
+                                           B, N, Kd, splits, _stream())
+    _lib.check(rc, "dots_gemm_skinny_bf16")
+    return out_bf16 if out_bf16 is not None else partial
+
+
+def pick_splits(n_tiles: int, num_kb: int, sms: int = 148) -> int:
+    """Largest valid split-K factor s with n_tiles * s <= sms (every split non-empty)."""
+    best = 1
+    for s in range(1, num_kb + 1):
+        per = -(-num_kb // s)
+        if -(-num_kb // per) != s:
+            continue
+        if n_tiles * s <= sms:
+            best = s
+    return best
+
+
+def attn_varlen(q, k, v, out, cu_seqlens, max_seqlen: int, n_q_heads: int, n_kv_heads: int, causal: bool,
+                scale: float, head_dim: int = 128):
+    """q/k/v/out: 2-D token-major views (may alias one fused qkv buffer)."""
+    for t in (q, k, v, out):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1
+    assert cu_seqlens.dtype == torch.int32 and cu_seqlens.is_cuda
+    rc = _lib.load().dots_attn_varlen_fwd(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),
+                                          _p(out), _ll(out.stride(0)), _p(cu_seqlens), cu_seqlens.numel() - 1,
+                                          int(max_seqlen), n_q_heads, n_kv_heads, head_dim, int(causal),
+                                          C.c_float(scale), _stream())
+    _lib.check(rc, "dots_attn_varlen_fwd")
+    return out
+
+
+def attn_decode(q, k_cache, v_cache, ctx_len, out, n_q_heads: int, n_kv_heads: int, ctx_max: int, n_splits: int,
+                scale: float, part_o=None, part_ml=None, head_dim: int = 128):
+    B = q.shape[0]
+    assert ctx_len.dtype == torch.int32
+    if n_splits > 1:
+        if part_o is None:
+            part_o = torch.empty((B, n_q_heads, n_splits, head_dim), device=q.device, dtype=torch.float32)
+        if part_ml is None:
+            part_ml = torch.empty((B, n_q_heads, n_splits, 2), device=q.device, dtype=torch.float32)
+    rc = _lib.load().dots_attn_decode(_p(q), _p(k_cache), _p(v_cache), _p(ctx_len), _p(out), _p(part_o), _p(part_ml),
+                                      B, n_q_heads, n_kv_heads, head_dim, _ll(ctx_max), n_splits, C.c_float(scale),
+                                      _stream())
+    _lib.check(rc, "dots_attn_decode")
+    return out
+
+
+def cast_pad(x: torch.Tensor, ldo: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.is_cuda and x.dim() == 2 and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, ldo), device=x.device, dtype=torch.bfloat16)
+    rc = _lib.load().dots_cast_pad_bf16(_p(x), int(x.dtype == torch.bfloat16), _ll(rows), cols, _p(out), ldo, _stream())
+    _lib.check(rc, "dots_cast_pad_bf16")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _bf16_2d(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.load().dots_rmsnorm(_p(x), _ll(x.stride(0)), _p(w), _p(out), _ll(out.stride(0)), _ll(x.shape[0]), x.shape[1],
+                                  C.c_float(eps), _stream())
+    _lib.check(rc, "dots_rmsnorm")
+    return out
+
+
+def layernorm(x, w, b, eps: float, out=None):
+    _bf16_2d(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.load().dots_layernorm(_p(x), _ll(x.stride(0)), _p(w), _p(b), _p(out), _ll(out.stride(0)), _ll(x.shape[0]),
+                                    x.shape[1], C.c_float(eps), _stream())
+    _lib.check(rc, "dots_layernorm")
+    return out
+
+
+def vit_rope_table(cu_seqlens, grid_hw, inv_freq, merge: int, total_tokens: int):
+    half = inv_freq.numel()
+    cos = torch.empty((total_tokens, 2 * half), device=cu_seqlens.device, dtype=torch.float32)
+    sin = torch.empty_like(cos)
+    rc = _lib.load().dots_vit_rope_table(_p(cu_seqlens), _p(grid_hw), grid_hw.shape[0], _p(inv_freq), half, merge, _p(cos),
+                                         _p(sin), total_tokens, _stream())
+    _lib.check(rc, "dots_vit_rope_table")
+    return cos, sin
+
+
+def vit_rope_apply(qkv: torch.Tensor, heads: int, cos, sin, head_dim: int = 128):
+    _bf16_2d(qkv, "qkv")
+    rc = _lib.load().dots_vit_rope_apply(_p(qkv), _ll(qkv.stride(0)), qkv.shape[0], heads, head_dim, _p(cos), _p(sin), _stream())
+    _lib.check(rc, "dots_vit_rope_apply")
+    return qkv
+
+
+def llm_rope_kv_append(qkv, n_q_heads, n_kv_heads, positions, seq_of_tok, inv_freq, k_cache, v_cache, ctx_max, head_dim=128):
+    _bf16_2d(qkv, "qkv")
+    assert positions.dtype == torch.int32 and seq_of_tok.dtype == torch.int32 and inv_freq.dtype == torch.float32
+    rc = _lib.load().dots_llm_rope_kv_append(_p(qkv), _ll(qkv.stride(0)), qkv.shape[0], n_q_heads, n_kv_heads, head_dim,
+                                             _p(positions), _p(seq_of_tok), _p(inv_freq), _p(k_cache), _p(v_cache),
+                                             _ll(ctx_max), _stream())
+    _lib.check(rc, "dots_llm_rope_kv_append")
+
+
+def image_slots(ids: torch.Tensor, image_token_id: int):
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
+    slots = torch.empty(ids.numel(), device=ids.device, dtype=torch.int32)
+    count = torch.zeros(1, device=ids.device, dtype=torch.int32)
+    rc = _lib.load().dots_image_slots(_p(ids), ids.numel(), _ll(image_token_id), _p(slots), _p(count), _stream())
+    _lib.check(rc, "dots_image_slots")
+    return slots, count
+
+
+def embed_scatter(ids, slots, table, img_embeds, out=None):
+    T = ids.numel()
+    V, H = table.shape
+    if out is None:
+        out = torch.empty((T, H), device=ids.device, dtype=torch.bfloat16)
+    rc = _lib.load().dots_embed_scatter(_p(ids), _p(slots), _p(table), _p(img_embeds), _p(out), T, H, _ll(V), _stream())
+    _lib.check(rc, "dots_embed_scatter")
+    return out
+
+
+def gather_rows(src, rows, out=None):
+    _bf16_2d(src, "src")
+    assert rows.dtype == torch.int32
+    n = rows.numel()
+    if out is None:
+        out = torch.empty((n, src.shape[1]), device=src.device, dtype=torch.bfloat16)
+    rc = _lib.load().dots_gather_rows(_p(src), _ll(src.stride(0)), _p(rows), _p(out), _ll(out.stride(0)), n, src.shape[1], _stream())
+    _lib.check(rc, "dots_gather_rows")
+    return out
+
+
+def argmax_advance(logits, next_ids, out_ids=None, step=None, pos=None, ctx_len=None, finished=None, eos_id: int = -1,
+                   pad_id: int = 0, forced_ids=None):
+    _bf16_2d(logits, "logits")
+    B, V = logits.shape
+    rc = _lib.load().dots_argmax_advance(_p(logits), _ll(logits.stride(0)), B, V, _p(next_ids), _p(out_ids),
+                                         _ll(out_ids.stride(0) if out_ids is not None else 0), _p(step), _p(pos), _p(ctx_len),
+                                         _p(finished), _ll(eos_id), _ll(pad_id), _p(forced_ids),
+                                         _ll(forced_ids.stride(0) if forced_ids is not None else 0), _stream())
+    _lib.check(rc, "dots_argmax_advance")
+
+
+def decode_embed_rmsnorm(ids, table, w, resid, normed, eps):
+    V, H = table.shape
+    rc = _lib.load().dots_decode_embed_rmsnorm(_p(ids), _p(table), _ll(V), _p(w), _p(resid), _p(normed), ids.numel(), H,
+                                               C.c_float(eps), _stream())
+    _lib.check(rc, "dots_decode_embed_rmsnorm")
+
+
+def decode_residual_rmsnorm(partial, splits, resid, w, normed, eps):
+    B, H = resid.shape
+    rc = _lib.load().dots_decode_residual_rmsnorm(_p(partial), splits, _p(resid), _p(w), _p(normed), B, H, C.c_float(eps), _stream())
+    _lib.check(rc, "dots_decode_residual_rmsnorm")
+
+
+def decode_qkv_rope_append(partial, splits, bias, pos, inv_freq, q_out, k_cache, v_cache, ctx_max, n_q_heads, n_kv_heads,
+                           head_dim=128):
+    B = q_out.shape[0]
+    rc = _lib.load().dots_decode_qkv_rope_append(_p(partial), splits, _p(bias), _p(pos), _p(inv_freq), _p(q_out), _p(k_cache),
+                                                 _p(v_cache), _ll(ctx_max), B, n_q_heads, n_kv_heads, head_dim, _stream())
+    _lib.check(rc, "dots_decode_qkv_rope_append")
+
+
+def decode_swiglu(partial, splits, act):
+    B, I = act.shape
+    rc = _lib.load().dots_decode_swiglu(_p(partial), splits, _p(act), B, I, _stream())
+    _lib.check(rc, "dots_decode_swiglu")
+
+
+class Graph:
+    """Capture the C-ABI launches issued inside the ``with`` block on the current stream."""
+
+    def __init__(self):
+        self.exec = _vp(0)
+
+    def __enter__(self):
+        _lib.check(_lib.load().dots_graph_begin(_stream()), "dots_graph_begin")
+        return self
+
+    def __exit__(self, et, ev, tb):
+        ex = _vp(0)
+        rc = _lib.load().dots_graph_end(_stream(), C.byref(ex))
+        if et is None:
+            _lib.check(rc, "dots_graph_end")
+            self.exec = ex
+        return False
+
+    def launch(self):
+        _lib.check(_lib.load().dots_graph_launch(self.exec, _stream()), "dots_graph_launch")
+
+    def __del__(self):
+        try:
+            if self.exec:
+                _lib.load().dots_graph_destroy(self.exec)
+        except Exception:
+            pass

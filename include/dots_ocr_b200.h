@@ -1,0 +1,149 @@
+/*
+ * dots_ocr_b200.h -- C ABI of libdots_ocr_b200.so: hand-written sm_100a kernels for the
+ * dots.ocr page-parsing hot path (ViT encode -> LLM prefill -> greedy decode).
+ *
+ * The reference (rednote-hilab/dots.ocr) has no FFI of its own: its seam is the Python call
+ * `self.model.generate(**inputs, max_new_tokens=N)` (dots_ocr/parser.py:110) whose arithmetic
+ * lives in HF remote code + torch/cuBLAS/flash-attn binaries.  Each entry point below replaces
+ * one of those library kernels; the citation names the reference-side operator it stands in for
+ * ([V] = vllm/model_executor/models/dots_ocr.py, [Q] = transformers/models/qwen2/modeling_qwen2.py,
+ * [G] = transformers/generation/utils.py -- the in-container mirrors SURVEY.md cites).
+ *
+ * Conventions: plain C types only; every pointer is a DEVICE pointer owned by the caller unless
+ * stated otherwise; `stream` is a cudaStream_t passed as void*; return 0 on success, negative on
+ * error (text via dots_last_error(), thread-local); no allocation and no synchronisation inside
+ * any call; bf16 tensors are row-major with explicit row pitch in ELEMENTS.
+ */
+#ifndef DOTS_OCR_B200_H
+#define DOTS_OCR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOTS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DOTS_API __attribute__((visibility("default")))
+#else
+#define DOTS_API
+#endif
+
+/* GEMM epilogues (rounding points follow HF eager: every nn.Linear output is rounded to bf16) */
+#define DOTS_EPI_STORE 0         /* out = bf16(acc) */
+#define DOTS_EPI_BIAS 1          /* out = bf16(acc + bias[n]) */
+#define DOTS_EPI_BIAS_GELU 2     /* out = bf16(gelu_erf(bf16(acc + bias[n])))          [V]:196-212 */
+#define DOTS_EPI_RESIDUAL 3      /* out = bf16(bf16(acc) + residual[m, n])             [V]:466,472  [Q]:302,308 */
+#define DOTS_EPI_SWIGLU 4        /* W rows interleaved per 256: [128 gate | 128 up];
+                                    out[m, N/2] = bf16(bf16(silu(bf16 g)) * bf16 u)     [V]:334-356  [Q]:46-48 */
+#define DOTS_EPI_F32_PARTIAL_T 5 /* internal: swap-AB split-K partials */
+#define DOTS_EPI_BF16_T 6        /* internal: swap-AB transposed bf16 store */
+
+DOTS_API const char* dots_last_error(void);
+DOTS_API int dots_abi_version(void);
+DOTS_API int dots_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- dense contractions (tcgen05 / TMEM / TMA) -------------------------------------------- */
+
+/* out[M, N(/2)] = epilogue(A[M, K] * W[N, K]^T).  Replaces every nn.Linear / Conv2d-as-GEMM on the
+ * prefill side: [V]:287 qkv, :315 proj, :334-356 fc1|fc3,fc2, :405-415 patch embed, :196-212 merger;
+ * [Q]:217-219 q/k/v (fused, +bias), :243 o_proj, :46-48 gate|up, down.  K, N, pitches % 8 == 0. */
+DOTS_API int dots_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                   int M, int N, int K, int epilogue, const void* bias, const void* residual, long long ldr,
+                   void* stream);
+
+/* Decode-time skinny GEMM (batch <= 256 rows), swap-AB so the weight matrix is the 128-row tensor-core
+ * operand and streams from HBM once.  Either
+ *   partial != NULL: partial[s][b][n] (fp32, s < splits) = sum over the s-th K slice, or
+ *   out_bf16 != NULL (splits must be 1): out_bf16[b, n] = bf16(acc (+ bias[n])).
+ * Replaces the M = batch nn.Linear calls of one decode step ([Q]:217-219, 243, 46-48, 474-475). */
+DOTS_API int dots_gemm_skinny_bf16(const void* X, long long ldx, const void* W, long long ldw, float* partial,
+                          void* out_bf16, long long ldo, const void* bias, int batch, int N, int K, int splits,
+                          void* stream);
+
+/* ---- attention ------------------------------------------------------------------------------ */
+
+/* Variable-length fused attention, head_dim 128.  q/k/v are token-major with per-token strides
+ * (elements) so they may alias a fused qkv buffer.  causal=0: ViT bidirectional per image
+ * ([V]:304-310, flash_attn_varlen_func); causal=1: LLM prefill, GQA ([Q]:161-183,227-241). */
+DOTS_API int dots_attn_varlen_fwd(const void* q, long long q_stride, const void* k, long long k_stride, const void* v,
+                         long long v_stride, void* out, long long o_stride, const int* cu_seqlens, int n_seqs,
+                         int max_seqlen, int n_q_heads, int n_kv_heads, int head_dim, int causal,
+                         float softmax_scale, void* stream);
+
+/* One-token-per-sequence attention over the KV cache [batch, n_kv_heads, ctx_max, 128]
+ * (replaces DynamicCache + sdpa/flash decode, transformers/cache_utils.py:102-120, [Q]:227-241).
+ * ctx_len[b] = number of visible keys (current token's key already appended).
+ * part_o [batch, n_q_heads, n_splits, 128] fp32 and part_ml [batch, n_q_heads, n_splits, 2] fp32 are
+ * scratch, required when n_splits > 1. */
+DOTS_API int dots_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* ctx_len, void* out,
+                     float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
+                     long long ctx_max, int n_splits, float softmax_scale, void* stream);
+
+/* ---- HBM-bound elementwise / reduction kernels ------------------------------------------------ */
+
+/* pixel_values [rows, cols] fp32 (or bf16) -> bf16 [rows, ldo] zero-padded ([V]:586 `.to(dtype)`). */
+DOTS_API int dots_cast_pad_bf16(const void* in, int in_is_bf16, long long rows, int cols, void* out, int ldo, void* stream);
+
+/* RMSNorm, fp32 statistics: out = bf16(bf16(x * rsqrt(mean x^2 + eps)) * w)   ([Q]:258-263, [V]:450,456,518). */
+DOTS_API int dots_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, long long rows, int cols,
+                 float eps, void* stream);
+
+/* LayerNorm with affine (PatchMerger.ln_q, [V]:190-191). */
+DOTS_API int dots_layernorm(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo,
+                   long long rows, int cols, float eps, void* stream);
+
+/* ViT 2-D rotary table: cos/sin [total_tokens, 64] fp32 from per-image grids (h, w) in 2x2-merge token
+ * order ([V]:163-174, 536-568).  grid_hw is [n_img, 2]; cu_seqlens [n_img + 1]; inv_freq [32]. */
+DOTS_API int dots_vit_rope_table(const int* cu_seqlens, const int* grid_hw, int n_img, const float* inv_freq, int half,
+                        int merge, float* cos_t, float* sin_t, int total_tokens, void* stream);
+
+/* In-place NeoX rotate-half (fp32 math) on the q and k thirds of qkv [S, 3*heads*128] ([V]:295-302). */
+DOTS_API int dots_vit_rope_apply(void* qkv, long long ld, int S, int heads, int head_dim, const float* cos_t,
+                        const float* sin_t, void* stream);
+
+/* LLM prefill: 1-D RoPE (bf16 arithmetic like HF, [Q]:102-146) in place on q,k of qkv [T, (nq+2nkv)*128]
+ * and append k, v at cache[seq_of_tok[t], :, positions[t]]  (cache_utils.py:119-120). */
+DOTS_API int dots_llm_rope_kv_append(void* qkv, long long ld, int T, int n_q_heads, int n_kv_heads, int head_dim,
+                            const int* positions, const int* seq_of_tok, const float* inv_freq, void* k_cache,
+                            void* v_cache, long long ctx_max, void* stream);
+
+/* masked_scatter bookkeeping: slots[t] = rank of token t among ids == image_token_id, else -1. */
+DOTS_API int dots_image_slots(const long long* ids, int T, long long image_token_id, int* slots, int* count_out, void* stream);
+
+/* out[t] = slots[t] >= 0 ? img_embeds[slots[t]] : table[ids[t]]   (embed_tokens + masked_scatter). */
+DOTS_API int dots_embed_scatter(const long long* ids, const int* slots, const void* table, const void* img_embeds, void* out,
+                       int T, int H, long long vocab, void* stream);
+
+DOTS_API int dots_gather_rows(const void* src, long long lds, const int* rows, void* out, long long ldo, int n, int cols,
+                     void* stream);
+
+/* Greedy step: argmax over bf16 logits in fp32, lowest index wins ties ([G]:2762,2793); finished rows emit
+ * pad, EOS marks finished ([G]:2796-2805); appends to out_ids[b, step[b]] and advances step/pos/ctx_len.
+ * forced_ids (optional) overrides the chosen token (teacher forcing for parity tests).  Nullable: out_ids,
+ * step, pos, ctx_len, finished, forced_ids.  eos_id < 0 disables EOS. */
+DOTS_API int dots_argmax_advance(const void* logits, long long ldl, int batch, int vocab, long long* next_ids,
+                        long long* out_ids, long long out_ld, int* step, int* pos, int* ctx_len, int* finished,
+                        long long eos_id, long long pad_id, const long long* forced_ids, long long forced_ld,
+                        void* stream);
+
+/* ---- decode-step fused finalize kernels (split-K reduce + HF rounding points) ------------------ */
+DOTS_API int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
+                              void* normed, int batch, int H, float eps, void* stream);
+DOTS_API int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed,
+                                 int batch, int H, float eps, void* stream);
+DOTS_API int dots_decode_qkv_rope_append(const float* partial, int splits, const void* bias, const int* pos,
+                                const float* inv_freq, void* q_out, void* k_cache, void* v_cache, long long ctx_max,
+                                int batch, int n_q_heads, int n_kv_heads, int head_dim, void* stream);
+DOTS_API int dots_decode_swiglu(const float* partial, int splits, void* act, int batch, int inter, void* stream);
+
+/* ---- CUDA-graph helpers (the decode step is captured once and replayed) ----------------------- */
+DOTS_API int dots_graph_begin(void* stream);
+DOTS_API int dots_graph_end(void* stream, void** graph_exec_out);
+DOTS_API int dots_graph_launch(void* graph_exec, void* stream);
+DOTS_API int dots_graph_destroy(void* graph_exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOTS_OCR_B200_H */
