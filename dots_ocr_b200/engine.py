@@ -235,6 +235,24 @@ class Engine:
         ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
                            st["eos"], st["pad"], st["forced"])
 
+    def decode_weight_bytes(self) -> int:
+        """bf16 bytes every decode step must stream: all decoder-layer weights + final norm + lm_head."""
+        n = self.final_norm.numel() + self.lm_head.numel()
+        for L in self.t_layers:
+            n += sum(v.numel() for v in L.values())
+        return 2 * n
+
+    def decode_bytes(self, B: int, seq_lens, n_steps: int) -> float:
+        """Algorithmic HBM bytes of `n_steps` decode steps: weights once per step + KV read of every visible
+        key + KV write of the new token (28 672 B per token per sequence at full size)."""
+        t = self.cfg.text
+        per_tok = 2 * t.num_hidden_layers * t.num_key_value_heads * t.head_dim * 2
+        total = float(n_steps) * self.decode_weight_bytes()
+        for L in seq_lens:
+            # step s (1-based) processes the token at position L + s - 1 and sees L + s keys
+            total += per_tok * (n_steps * L + n_steps * (n_steps + 1) / 2.0) + per_tok * n_steps
+        return total
+
     def launches_per_decode_step(self, B: int) -> int:
         pl = self._decode_plan(B)
         per_layer = 9 + (1 if pl["attn"] > 1 else 0)
@@ -318,6 +336,10 @@ class Engine:
 
         n_steps = N - 1
         per_step = self.launches_per_decode_step(B)
+        prof_ev = None
+        if ops.PROFILE is not None and n_steps > 0:
+            prof_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            prof_ev[0].record()
         if n_steps > 0:
             if use_graph and not return_logits:
                 self._decode_step(st)                   # eager once (also warms every kernel variant)
@@ -343,6 +365,9 @@ class Engine:
                         all_logits[s + 1].copy_(st["logits"])
                 self.launches += per_step * n_steps
 
+        if prof_ev is not None:
+            prof_ev[1].record()
+            ops.PROFILE.append(("decode_phase", self.decode_bytes(B, seq_lens, n_steps), prof_ev[0], prof_ev[1]))
         out_new = st["out_ids"]
         if eos_token_id is not None:
             fin_step = (out_new == int(eos_token_id)).int().argmax(dim=1)

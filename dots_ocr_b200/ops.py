@@ -17,6 +17,30 @@ EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_SWIGLU = (
 _ll = C.c_longlong
 _vp = C.c_void_p
 
+# Optional profiling hook (bench.py): when a list, selected launches are bracketed by CUDA events on the
+# launching stream and (kernel name, algorithmic work, start, end) is appended.
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, name: str, work: float):
+        self.on = PROFILE is not None
+        if self.on:
+            self.name, self.work = name, work
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            PROFILE.append((self.name, self.work, self.e0, self.e1))
+        return False
+
 
 def _stream() -> _vp:
     return _vp(torch.cuda.current_stream().cuda_stream)
@@ -44,8 +68,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, e
     _bf16_2d(out, "out")
     assert out.shape == (M, n_out), (out.shape, M, n_out)
     ldr = residual.stride(0) if residual is not None else 0
-    rc = _lib.load().dots_gemm_bf16(_p(a), _ll(a.stride(0)), _p(w), _ll(w.stride(0)), _p(out), _ll(out.stride(0)),
-                                    M, N, Kd, epilogue, _p(bias), _p(residual), _ll(ldr), _stream())
+    with _Prof("gemm_bf16_tcgen05", 2.0 * M * N * Kd):
+        rc = _lib.load().dots_gemm_bf16(_p(a), _ll(a.stride(0)), _p(w), _ll(w.stride(0)), _p(out), _ll(out.stride(0)),
+                                        M, N, Kd, epilogue, _p(bias), _p(residual), _ll(ldr), _stream())
     _lib.check(rc, "dots_gemm_bf16")
     return out
 
@@ -86,10 +111,15 @@ def attn_varlen(q, k, v, out, cu_seqlens, max_seqlen: int, n_q_heads: int, n_kv_
     for t in (q, k, v, out):
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1
     assert cu_seqlens.dtype == torch.int32 and cu_seqlens.is_cuda
-    rc = _lib.load().dots_attn_varlen_fwd(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),
-                                          _p(out), _ll(out.stride(0)), _p(cu_seqlens), cu_seqlens.numel() - 1,
-                                          int(max_seqlen), n_q_heads, n_kv_heads, head_dim, int(causal),
-                                          C.c_float(scale), _stream())
+    work = 0.0
+    if PROFILE is not None:        # algorithmic FLOPs: 4 * L^2 * d per head (half that when causal)
+        lens = (cu_seqlens[1:] - cu_seqlens[:-1]).double()
+        work = float((lens * lens).sum().item()) * 4.0 * head_dim * n_q_heads * (0.5 if causal else 1.0)
+    with _Prof("attn_fwd_prefill" if causal else "attn_fwd_vit", work):
+        rc = _lib.load().dots_attn_varlen_fwd(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),
+                                              _p(out), _ll(out.stride(0)), _p(cu_seqlens), cu_seqlens.numel() - 1,
+                                              int(max_seqlen), n_q_heads, n_kv_heads, head_dim, int(causal),
+                                              C.c_float(scale), _stream())
     _lib.check(rc, "dots_attn_varlen_fwd")
     return out
 

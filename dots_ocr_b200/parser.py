@@ -1,0 +1,142 @@
+"""``DotsOCRParser`` with the reference's constructor and public methods
+(``dots_ocr/parser.py:22-36, 255-322``), its model call served by the B200 engine.
+
+Only the hot-path seam is re-implemented here: ``_load_hf_model`` / ``_inference_with_hf`` /
+``_inference_with_vllm`` / ``get_prompt`` / ``parse_image`` / ``parse_file``.  The CPU
+post-processing of the decoded text (layout JSON repair, markdown, drawing)
+and PDF rasterisation (row 9, needs PyMuPDF) are out of scope for this tier: results are saved
+as the raw response plus, when it parses, the JSON.  See INTEGRATION.md for patching the
+reference's own parser instead.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import List, Optional
+
+from .model.inference import inference_with_vllm
+from .utils.consts import MIN_PIXELS, MAX_PIXELS, image_extensions
+from .utils.image_utils import smart_resize
+from .utils.prompts import dict_promptmode_to_prompt
+
+
+class DotsOCRParser:
+    """parse image or pdf file"""
+
+    def __init__(self,
+                 protocol='http',
+                 ip='localhost',
+                 port=8000,
+                 model_name='model',
+                 temperature=0.1,
+                 top_p=1.0,
+                 max_completion_tokens=16384,
+                 num_thread=64,
+                 dpi=200,
+                 output_dir="./output",
+                 min_pixels=None,
+                 max_pixels=None,
+                 use_hf=False,
+                 runner=None,
+                 ):
+        self.dpi = dpi
+        self.protocol, self.ip, self.port, self.model_name = protocol, ip, port, model_name
+        self.temperature, self.top_p = temperature, top_p
+        self.max_completion_tokens = max_completion_tokens
+        self.num_thread = num_thread
+        self.output_dir = output_dir
+        self.min_pixels, self.max_pixels = min_pixels, max_pixels
+        self.use_hf = use_hf
+        self._runner = runner
+        if self.use_hf:
+            self._load_hf_model()
+        assert self.min_pixels is None or self.min_pixels >= MIN_PIXELS
+        assert self.max_pixels is None or self.max_pixels <= MAX_PIXELS
+
+    # -- model adapter ------------------------------------------------------------------------
+    def _load_hf_model(self):
+        """Reference: AutoModelForCausalLM + AutoProcessor from ./weights/DotsOCR (parser.py:62-76).
+        Here: the in-process B200 engine (real checkpoint directory if present, else synthetic)."""
+        if self._runner is None:
+            from .model.inference import get_default_runner
+            self._runner = get_default_runner()
+        self.model = self._runner.engine
+        self.processor = self._runner.tokenizer
+
+    def _inference_with_hf(self, image, prompt):
+        if self._runner is None:
+            self._load_hf_model()
+        return self._runner.infer(image, prompt, max_new_tokens=min(24000, self.max_completion_tokens))
+
+    def _inference_with_vllm(self, image, prompt):
+        if self._runner is not None:
+            return self._runner.infer(image, prompt, max_new_tokens=self.max_completion_tokens)
+        return inference_with_vllm(image, prompt, model_name=self.model_name, protocol=self.protocol, ip=self.ip,
+                                   port=self.port, temperature=self.temperature, top_p=self.top_p,
+                                   max_completion_tokens=self.max_completion_tokens)
+
+    def get_prompt(self, prompt_mode, bbox=None, origin_image=None, image=None, min_pixels=None, max_pixels=None):
+        prompt = dict_promptmode_to_prompt[prompt_mode]
+        if prompt_mode == 'prompt_grounding_ocr':
+            assert bbox is not None
+            # bbox is given in origin_image pixels; the model sees the smart_resize'd image (layout_utils.py:115-144)
+            h, w = smart_resize(image.height, image.width, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
+            sx, sy = w / origin_image.width, h / origin_image.height
+            x1, y1, x2, y2 = bbox
+            prompt = prompt + str([int(x1 * sx), int(y1 * sy), int(x2 * sx), int(y2 * sy)])
+        return prompt
+
+    # -- pages --------------------------------------------------------------------------------
+    def _parse_single_image(self, origin_image, prompt_mode, save_dir, save_name, source="image", page_idx=0, bbox=None):
+        min_pixels, max_pixels = self.min_pixels, self.max_pixels
+        if prompt_mode == "prompt_grounding_ocr":
+            min_pixels = min_pixels or MIN_PIXELS
+            max_pixels = max_pixels or MAX_PIXELS
+        from .processing import to_rgb
+        image = to_rgb(origin_image)
+        prompt = self.get_prompt(prompt_mode, bbox, origin_image, image, min_pixels=min_pixels, max_pixels=max_pixels)
+        response = self._inference_with_hf(image, prompt) if self.use_hf else self._inference_with_vllm(image, prompt)
+        result = {'page_no': page_idx, 'input_height': image.height, 'input_width': image.width}
+        if source == 'pdf':
+            save_name = f"{save_name}_page_{page_idx}"
+        os.makedirs(save_dir, exist_ok=True)
+        try:
+            cells = json.loads(response)
+            path = os.path.join(save_dir, f"{save_name}.json")
+            with open(path, 'w', encoding='utf-8') as w:
+                json.dump(cells, w, ensure_ascii=False)
+            result['layout_info_path'] = path
+        except (TypeError, ValueError):
+            result['filtered'] = True
+        md_path = os.path.join(save_dir, f"{save_name}.md")
+        with open(md_path, 'w', encoding='utf-8') as w:
+            w.write(response if response is not None else "")
+        result['md_content_path'] = md_path
+        return result
+
+    def parse_image(self, input_path, filename, prompt_mode, save_dir, bbox=None):
+        from PIL import Image
+        origin_image = input_path if isinstance(input_path, Image.Image) else Image.open(input_path)
+        result = self._parse_single_image(origin_image, prompt_mode, save_dir, filename, source="image", bbox=bbox)
+        result['file_path'] = input_path if isinstance(input_path, str) else filename
+        return [result]
+
+    def parse_pdf(self, input_path, filename, prompt_mode, save_dir):
+        raise NotImplementedError("PDF rasterisation (PyMuPDF, dots_ocr/utils/doc_utils.py:42-60) is outside the hot-path "
+                                  "scope; rasterise pages to images and call parse_image")
+
+    def parse_file(self, input_path, output_dir="", prompt_mode="prompt_layout_all_en", bbox=None):
+        output_dir = os.path.abspath(output_dir or self.output_dir)
+        filename, file_ext = os.path.splitext(os.path.basename(input_path))
+        save_dir = os.path.join(output_dir, filename)
+        os.makedirs(save_dir, exist_ok=True)
+        if file_ext == '.pdf':
+            results = self.parse_pdf(input_path, filename, prompt_mode, save_dir)
+        elif file_ext in image_extensions:
+            results = self.parse_image(input_path, filename, prompt_mode, save_dir, bbox=bbox)
+        else:
+            raise ValueError(f"file extension {file_ext} not supported, supported extensions are {image_extensions} and pdf")
+        with open(os.path.join(output_dir, os.path.basename(filename) + '.jsonl'), 'w', encoding='utf-8') as w:
+            for result in results:
+                w.write(json.dumps(result, ensure_ascii=False) + '\n')
+        return results

@@ -1,0 +1,105 @@
+"""Host-side input contract of the hot path: PIL image + prompt -> the tensors ``generate`` takes.
+
+Restates the stock ``Qwen2VLImageProcessor`` (fast/torchvision variant the reference selects with
+``use_fast=True``, ``dots_ocr/parser.py:75``) for the dots.ocr settings: patch 14, merge 2,
+temporal_patch_size 1, CLIP mean/std, bicubic + antialias resize on the uint8 tensor
+(``transformers/models/qwen2_vl/image_processing_qwen2_vl.py:148-232``).  ``tests/test_processing.py``
+checks bit-equality with the transformers class on the reference's demo images.
+
+The chat template and tokenizer live in the HF checkpoint directory, which does not exist offline;
+``SyntheticTokenizer`` is a byte-level stand-in used only to exercise the plumbing.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .utils.consts import MIN_PIXELS, MAX_PIXELS
+from .utils.image_utils import smart_resize
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+IMAGE_PLACEHOLDER = "<|img|><|imgpad|><|endofimg|>"      # dots_ocr/model/inference.py:33
+
+
+def to_rgb(pil_image):
+    """RGBA is composited on white, everything else converted (reference image_utils.py:74-80)."""
+    from PIL import Image
+    if pil_image.mode == "RGBA":
+        bg = Image.new("RGB", pil_image.size, (255, 255, 255))
+        bg.paste(pil_image, mask=pil_image.split()[3])
+        return bg
+    return pil_image.convert("RGB")
+
+
+def preprocess_image(image, min_pixels: Optional[int] = None, max_pixels: Optional[int] = None,
+                     patch: int = 14, merge: int = 2) -> Tuple[torch.Tensor, torch.Tensor]:
+    """PIL image (or uint8 HWC array) -> (pixel_values [gh*gw, 3*patch*patch] fp32, grid_thw [1, 3] int64).
+    Rows are in 2x2 merge-block order; each row is channel-major (c, py, px)."""
+    import torchvision.transforms.v2.functional as tvF
+    from torchvision.transforms import InterpolationMode
+    if not isinstance(image, (np.ndarray, torch.Tensor)):
+        image = np.asarray(to_rgb(image))
+    img = torch.from_numpy(np.array(image, copy=True))
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3, "expect uint8 HWC RGB"
+    img = img.permute(2, 0, 1).contiguous()                                 # CHW
+    H, W = img.shape[1:]
+    rh, rw = smart_resize(H, W, factor=patch * merge, min_pixels=min_pixels or MIN_PIXELS,
+                          max_pixels=max_pixels or MAX_PIXELS)
+    if (rh, rw) != (H, W):
+        img = tvF.resize(img, [rh, rw], interpolation=InterpolationMode.BICUBIC, antialias=True)
+    x = img.to(torch.float32)
+    # the fast processor fuses rescale into the normalisation: (x - 255*mean) / (255*std)
+    mean = torch.tensor(CLIP_MEAN, dtype=torch.float32) * 255.0
+    std = torch.tensor(CLIP_STD, dtype=torch.float32) * 255.0
+    x = (x - mean[:, None, None]) / std[:, None, None]
+    gh, gw = rh // patch, rw // patch
+    x = x.view(3, gh // merge, merge, patch, gw // merge, merge, patch)
+    x = x.permute(1, 4, 2, 5, 0, 3, 6).reshape(gh * gw, 3 * patch * patch)   # (bh, bw, ih, iw | c, py, px)
+    return x.contiguous(), torch.tensor([[1, gh, gw]], dtype=torch.int64)
+
+
+class SyntheticTokenizer:
+    """Byte-level stand-in (ids 0..255 = bytes) with the three image specials mapped onto the config's
+    reserved ids.  NOT the dots.ocr tokenizer: decoded text is meaningless with synthetic weights."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.image_token_id = cfg.image_token_id
+        self.img_start_id = cfg.image_token_id - 2
+        self.img_end_id = cfg.image_token_id - 1
+        self.user_id, self.end_user_id, self.assistant_id = (cfg.image_token_id - 5, cfg.image_token_id - 4,
+                                                             cfg.image_token_id - 3)
+        self.eos_token_id = None
+        self.pad_token_id = 0
+
+    def encode_chat(self, prompt: str, n_image_tokens: int) -> List[int]:
+        """<|user|><|img|><|imgpad|>*n<|endofimg|>{prompt}<|endofuser|><|assistant|>."""
+        ids = [self.user_id, self.img_start_id] + [self.image_token_id] * n_image_tokens + [self.img_end_id]
+        ids += list(prompt.encode("utf-8"))
+        ids += [self.end_user_id, self.assistant_id]
+        return ids
+
+    def decode(self, ids: Sequence[int]) -> str:
+        return bytes(int(i) for i in ids if 0 <= int(i) < 256).decode("utf-8", errors="replace")
+
+
+def build_inputs(tokenizer: SyntheticTokenizer, images: Sequence, prompts: Sequence[str], min_pixels=None, max_pixels=None,
+                 merge: int = 2):
+    """What ``processor(text=[...], images=[...], padding=True, return_tensors="pt")`` returns
+    (parser.py:99-105): left-padded input_ids + attention_mask, concatenated pixel_values, grid_thw."""
+    pvs, grids, rows = [], [], []
+    for img, prompt in zip(images, prompts):
+        pv, g = preprocess_image(img, min_pixels, max_pixels, merge=merge)
+        pvs.append(pv)
+        grids.append(g)
+        rows.append(tokenizer.encode_chat(prompt, pv.shape[0] // (merge * merge)))
+    T = max(len(r) for r in rows)
+    ids = torch.full((len(rows), T), tokenizer.pad_token_id, dtype=torch.int64)
+    mask = torch.zeros((len(rows), T), dtype=torch.int64)
+    for i, r in enumerate(rows):
+        ids[i, T - len(r):] = torch.tensor(r)
+        mask[i, T - len(r):] = 1
+    return dict(input_ids=ids, attention_mask=mask, pixel_values=torch.cat(pvs), image_grid_thw=torch.cat(grids))

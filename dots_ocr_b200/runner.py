@@ -1,0 +1,56 @@
+"""PageRunner: image + prompt -> generated text on one GPU.
+
+This is the body that replaces ``DotsOCRParser._load_hf_model`` / ``_inference_with_hf``
+(``dots_ocr/parser.py:62-117``): processor call -> H2D -> ``generate`` -> trim prompt -> decode.
+A lock serialises callers (the reference fans pages out from up to 64 threads,
+``parser.py:282-290``; the C ABI is re-entrant per stream, not per engine object).
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import config as _config
+from . import weights as _weights
+from .processing import SyntheticTokenizer, build_inputs
+
+
+class PageRunner:
+    def __init__(self, engine, tokenizer, min_pixels=None, max_pixels=None, max_new_tokens_cap: int = 24000):
+        self.engine = engine
+        self.tokenizer = tokenizer
+        self.min_pixels = min_pixels
+        self.max_pixels = max_pixels
+        self.cap = max_new_tokens_cap
+        self._lock = threading.Lock()
+
+    @classmethod
+    def from_default(cls, device: str = "cuda:0", weights_dir: str = "./weights/DotsOCR", preset: Optional[str] = None):
+        """Real checkpoint if ``./weights/DotsOCR`` exists (parser.py:67), else the seeded synthetic one."""
+        from .engine import Engine
+        preset = preset or os.environ.get("DOTS_B200_PRESET", "full")
+        cfg = _config.PRESETS[preset]()
+        if os.path.isdir(weights_dir):
+            ckpt = _weights.load_safetensors_dir(weights_dir, device=device)
+        else:
+            ckpt = _weights.make_synthetic_checkpoint(cfg, 0, "peaked", device=device)
+        return cls(Engine(cfg, ckpt, device), SyntheticTokenizer(cfg))
+
+    def infer_batch(self, images: Sequence, prompts: Sequence[str], max_new_tokens: int = 512) -> List[str]:
+        inputs = build_inputs(self.tokenizer, images, prompts, self.min_pixels, self.max_pixels)
+        n_new = max(1, min(int(max_new_tokens), self.cap))
+        with self._lock:
+            dev = self.engine.device
+            out = self.engine.generate(input_ids=inputs["input_ids"].to(dev), attention_mask=inputs["attention_mask"].to(dev),
+                                       pixel_values=inputs["pixel_values"].to(dev), image_grid_thw=inputs["image_grid_thw"],
+                                       max_new_tokens=n_new, eos_token_id=self.tokenizer.eos_token_id,
+                                       pad_token_id=self.tokenizer.pad_token_id)
+            seq = out.sequences.cpu()
+        T = inputs["input_ids"].shape[1]
+        return [self.tokenizer.decode(row[T:].tolist()) for row in seq]          # trim the prompt (parser.py:111-113)
+
+    def infer(self, image, prompt: str, max_new_tokens: int = 512) -> str:
+        return self.infer_batch([image], [prompt], max_new_tokens)[0]

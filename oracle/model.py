@@ -28,13 +28,13 @@ def build_qwen2(tcfg, ckpt: Dict[str, torch.Tensor], dtype, device, attn_impl: s
     missing, unexpected = m.load_state_dict(sd, strict=False, assign=True)
     assert not unexpected, unexpected
     assert all("rotary" in k or "inv_freq" in k for k in missing), missing
-    # rotary inv_freq buffers are non-persistent: rebuild them on the right device
+    # rotary inv_freq is a non-persistent fp32 buffer: to_empty() left it uninitialised and .to(dtype)
+    # would round it; rebuild it exactly as Qwen2RotaryEmbedding.__init__ does (modeling_qwen2.py:54-68).
     rot = m.model.rotary_emb
-    inv, _ = rot.rope_init_fn(rot.config, device) if hasattr(rot, "rope_init_fn") else (None, None)
-    if inv is not None:
-        rot.inv_freq = inv.to(device)
-        if hasattr(rot, "original_inv_freq"):
-            rot.original_inv_freq = inv.to(device).clone()
+    inv, scaling = rot.compute_default_rope_parameters(rot.config, device)
+    rot.inv_freq = inv.to(device=device, dtype=torch.float32)
+    rot.original_inv_freq = rot.inv_freq.clone()
+    rot.attention_scaling = scaling
     return m.eval()
 
 

@@ -1,0 +1,251 @@
+"""CPU suite: oracle vs golden vectors, host logic, and the C-ABI library's exported surface."""
+import ctypes
+import inspect
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+# ------------------------------------------------------------------ smart_resize (pinned against the reference itself)
+def test_smart_resize_matches_reference_golden():
+    from dots_ocr_b200.utils.image_utils import smart_resize
+    cases = json.load(open(os.path.join(GOLD, "smart_resize.json")))
+    assert len(cases) > 1000
+    for c in cases:
+        try:
+            got = list(smart_resize(c["h"], c["w"], **c["kw"]))
+        except ValueError:
+            got = "ValueError"
+        assert got == c["out"], c
+
+
+def test_token_counts_of_the_baseline_pages():
+    from dots_ocr_b200.utils.image_utils import smart_resize, token_counts
+    assert smart_resize(1024, 1024) == (1036, 1036)
+    assert token_counts(1024, 1024) == (5476, 1369)
+    assert token_counts(1960, 1960) == (19600, 4900)
+    assert token_counts(2250, 1700) == (19520, 4880)          # demo_image1.jpg (h, w)
+    assert token_counts(3360, 3360) == (57600, 14400)         # MAX_PIXELS
+    with pytest.raises(ValueError):
+        smart_resize(10, 2001)
+
+
+# ------------------------------------------------------------------ image pre-processing vs the stock HF processor
+def test_preprocess_image_equals_hf_processor():
+    from PIL import Image
+    from transformers import Qwen2VLImageProcessor
+    from dots_ocr_b200.processing import preprocess_image
+    rng = np.random.default_rng(5)
+    proc = Qwen2VLImageProcessor(patch_size=14, temporal_patch_size=1, merge_size=2,
+                                 size={"shortest_edge": 3136, "longest_edge": 11289600})
+    for (h, w) in [(300, 200), (1024, 1024), (57, 400)]:
+        arr = np.full((h, w, 3), 255, np.uint8)
+        for _ in range(30):                                  # document-like: dark rectangles on white
+            y, x = rng.integers(0, h - 4), rng.integers(0, w - 4)
+            arr[y:y + rng.integers(2, 40), x:x + rng.integers(2, 120)] = rng.integers(0, 90, 3)
+        im = Image.fromarray(arr)
+        ref = proc(images=[im], return_tensors="pt")
+        pv, grid = preprocess_image(im)
+        assert torch.equal(grid, ref["image_grid_thw"])
+        assert torch.equal(pv, ref["pixel_values"])
+    pv, grid = preprocess_image(Image.fromarray(np.zeros((1024, 1024, 3), np.uint8)))
+    assert pv.shape == (5476, 588) and grid.tolist() == [[1, 74, 74]]
+
+
+def test_build_inputs_left_pads_and_counts_image_tokens():
+    from PIL import Image
+    from dots_ocr_b200 import config
+    from dots_ocr_b200.processing import SyntheticTokenizer, build_inputs
+    cfg = config.tiny()
+    tok = SyntheticTokenizer(cfg)
+    ims = [Image.new("RGB", (112, 112), "white"), Image.new("RGBA", (56, 168), (0, 0, 0, 0))]
+    out = build_inputs(tok, ims, ["hello", "a longer prompt"])
+    assert out["pixel_values"].shape[1] == 588
+    n_img = int((out["input_ids"] == cfg.image_token_id).sum())
+    assert n_img == out["pixel_values"].shape[0] // 4
+    assert out["attention_mask"][0, 0] == 0 or out["attention_mask"][1, 0] == 0       # the shorter row is left-padded
+    assert (out["attention_mask"][:, -1] == 1).all()
+    assert tok.decode(tok.encode_chat("héllo", 0)) == "héllo"
+
+
+# ------------------------------------------------------------------ oracle
+def test_oracle_decoder_is_stock_hf_qwen2():
+    """build_qwen2 (meta init + assign) must equal a normally constructed Qwen2ForCausalLM with the same weights
+    (regression: non-persistent rotary inv_freq must be rebuilt in fp32)."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    from dots_ocr_b200 import config, weights
+    from oracle.model import build_qwen2
+    t = config.tiny().text
+    ck = weights.make_synthetic_checkpoint(config.tiny(), 0, "random")
+    m = build_qwen2(t, ck, torch.float32, torch.device("cpu"))
+    hf = Qwen2Config(vocab_size=t.vocab_size, hidden_size=t.hidden_size, intermediate_size=t.intermediate_size,
+                     num_hidden_layers=t.num_hidden_layers, num_attention_heads=t.num_attention_heads,
+                     num_key_value_heads=t.num_key_value_heads, max_position_embeddings=t.max_position_embeddings,
+                     rms_norm_eps=t.rms_norm_eps, rope_theta=t.rope_theta, tie_word_embeddings=False, attn_implementation="sdpa")
+    m2 = Qwen2ForCausalLM(hf).eval()
+    m2.load_state_dict({k: v.float() for k, v in ck.items() if not k.startswith("vision_tower.")}, strict=True)
+    ids = torch.randint(0, 2000, (2, 33), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        assert torch.equal(m(input_ids=ids).logits, m2(input_ids=ids).logits)
+    mb = build_qwen2(t, ck, torch.bfloat16, torch.device("cpu"))
+    assert mb.model.rotary_emb.inv_freq.dtype == torch.float32
+    assert torch.equal(mb.model.rotary_emb.inv_freq, m2.model.rotary_emb.inv_freq)
+
+
+def test_oracle_matches_golden_vectors():
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_oracle_golden import golden_inputs, N_NEW
+    from dots_ocr_b200 import config, weights
+    from oracle.model import DotsOracle
+    cfg = config.tiny()
+    gold = np.load(os.path.join(GOLD, "oracle_tiny.npz"))
+    pv, grid, ids, mask = golden_inputs(cfg)
+    for fl in ("peaked", "random"):
+        ck = weights.make_synthetic_checkpoint(cfg, 0, fl)
+        o = DotsOracle(cfg, ck, torch.float32, "cpu")
+        img = o.vision.forward(pv, grid)
+        ref = torch.from_numpy(gold[f"{fl}_image_embeds"])
+        assert float((img - ref).abs().max() / ref.abs().max()) < 1e-4
+        if fl == "peaked":            # well-posed argmax: ids are reproducible across BLAS builds / thread counts
+            seq = o.generate(ids, attention_mask=mask, pixel_values=pv, image_grid_thw=grid, max_new_tokens=N_NEW)
+            assert np.array_equal(seq.numpy(), gold["peaked_sequences"])
+            T = ids.shape[1]
+            for b in range(ids.shape[0]):     # and they follow the successor map baked into the checkpoint
+                chain = [int(ids[b, -1])]
+                for _ in range(N_NEW):
+                    chain.append(weights.peaked_next_token(cfg, chain[-1]))
+                assert seq[b, T:].tolist() == chain[1:]
+
+
+def test_vision_pos_ids_and_rope_known_answers():
+    from oracle.vision import vision_pos_ids, rot_pos_emb
+    p = vision_pos_ids([[1, 4, 4]], 2)
+    # first merge block = (0,0),(0,1),(1,0),(1,1); second block starts at column 2
+    assert p[:4].tolist() == [[0, 0], [0, 1], [1, 0], [1, 1]]
+    assert p[4:8].tolist() == [[0, 2], [0, 3], [1, 2], [1, 3]]
+    assert p[8].tolist() == [2, 0]
+    ang = rot_pos_emb([[1, 4, 6]], 2, 128, 10000.0, "cpu")
+    assert ang.shape == (24, 64)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    pos = vision_pos_ids([[1, 4, 6]], 2)
+    assert torch.equal(ang[:, :32], pos[:, :1].float() * inv) and torch.equal(ang[:, 32:], pos[:, 1:].float() * inv)
+
+
+def test_teacher_forced_logits_reproduce_generate():
+    from dots_ocr_b200 import config, weights
+    from oracle.model import DotsOracle
+    cfg = config.tiny()
+    o = DotsOracle(cfg, weights.make_synthetic_checkpoint(cfg, 0, "random"))
+    ids = torch.randint(0, 2000, (2, 9), generator=torch.Generator().manual_seed(4))
+    seq = o.generate(ids, max_new_tokens=5)
+    lg = o.teacher_forced_logits(ids, seq[:, 9:])
+    assert torch.equal(lg.argmax(-1), seq[:, 9:])
+
+
+# ------------------------------------------------------------------ host logic
+def test_param_counts_match_the_survey():
+    from dots_ocr_b200 import config, weights
+    c = weights.param_count(config.full())
+    assert c["vision"] == 1_262_091_264 and c["text"] == 1_777_088_000       # 1.2621 B / 1.7771 B
+    names = weights.tensor_names(config.full())
+    assert "vision_tower.blocks.41.mlp.fc3.weight" in names and "model.layers.27.self_attn.q_proj.bias" in names
+
+
+def test_pick_splits_is_valid_and_fills_the_sms():
+    from dots_ocr_b200.ops import pick_splits
+    for tiles, kb in [(16, 24), (12, 24), (12, 140), (140, 24), (1187, 24), (8, 12), (6, 16), (1, 1), (3, 7)]:
+        s = pick_splits(tiles, kb, 148)
+        per = -(-kb // s)
+        assert -(-kb // per) == s and tiles * s <= max(148, tiles)
+    assert pick_splits(12, 140) == 12 and pick_splits(140, 24) == 1
+
+
+def test_gate_up_interleave_layout():
+    from dots_ocr_b200.engine import _interleave_gate_up
+    g = torch.arange(256 * 2, dtype=torch.float32).reshape(256, 2)
+    u = -g
+    w = _interleave_gate_up(g, u)
+    assert w.shape == (512, 2)
+    assert torch.equal(w[:128], g[:128]) and torch.equal(w[128:256], u[:128])
+    assert torch.equal(w[256:384], g[128:]) and torch.equal(w[384:], u[128:])
+
+
+def test_engine_refuses_cpu_and_missing_library(monkeypatch):
+    from dots_ocr_b200 import config, _lib
+    from dots_ocr_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(config.tiny(), {}, "cpu")
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdots_ocr_b200.so")
+    with pytest.raises(_lib.DotsLibraryError):
+        _lib.load()
+
+
+def test_parser_keeps_the_reference_constructor_surface():
+    from dots_ocr_b200 import DotsOCRParser
+    from dots_ocr_b200.model.inference import inference_with_vllm
+    ref_ctor = ["protocol", "ip", "port", "model_name", "temperature", "top_p", "max_completion_tokens", "num_thread", "dpi",
+                "output_dir", "min_pixels", "max_pixels", "use_hf"]                       # dots_ocr/parser.py:22-36
+    got = list(inspect.signature(DotsOCRParser.__init__).parameters)[1:]
+    assert got[: len(ref_ctor)] == ref_ctor
+    sig = inspect.signature(DotsOCRParser.__init__).parameters
+    assert sig["temperature"].default == 0.1 and sig["top_p"].default == 1.0 and sig["max_completion_tokens"].default == 16384
+    assert sig["num_thread"].default == 64 and sig["dpi"].default == 200 and sig["use_hf"].default is False
+    ref_inf = ["image", "prompt", "protocol", "ip", "port", "temperature", "top_p", "max_completion_tokens", "model_name",
+               "system_prompt"]                                                            # dots_ocr/model/inference.py:7-18
+    assert list(inspect.signature(inference_with_vllm).parameters) == ref_inf
+    for m in ("parse_file", "parse_image", "parse_pdf", "get_prompt", "_inference_with_hf", "_inference_with_vllm"):
+        assert hasattr(DotsOCRParser, m)
+    from dots_ocr_b200.utils import dict_promptmode_to_prompt
+    assert len(dict_promptmode_to_prompt) == 8 and "prompt_layout_all_en" in dict_promptmode_to_prompt
+
+
+def test_parser_plumbing_with_a_fake_runner(tmp_path):
+    from PIL import Image
+    from dots_ocr_b200 import DotsOCRParser
+
+    class Fake:
+        def infer(self, image, prompt, max_new_tokens=0):
+            self.seen = (image.size, prompt, max_new_tokens)
+            return '[{"bbox": [1, 2, 3, 4], "category": "Text", "text": "x"}]'
+    fake = Fake()
+    p = DotsOCRParser(output_dir=str(tmp_path), runner=fake)
+    img = tmp_path / "page.png"
+    Image.new("RGBA", (120, 90), (255, 0, 0, 128)).save(img)
+    res = p.parse_file(str(img), prompt_mode="prompt_layout_only_en")
+    assert res[0]["page_no"] == 0 and os.path.exists(res[0]["layout_info_path"]) and os.path.exists(res[0]["md_content_path"])
+    assert fake.seen[0] == (120, 90) and "layout" in fake.seen[1]
+    with pytest.raises(ValueError):
+        p.parse_file(str(tmp_path / "x.tiff"))
+
+
+# ------------------------------------------------------------------ C ABI surface (no GPU compute)
+def test_library_exports_every_declared_symbol():
+    from dots_ocr_b200 import _lib
+    lib = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.dots_abi_version() == _lib.header_constants()["DOTS_ABI_VERSION"]
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    from dots_ocr_b200 import _lib
+    lib = _lib.load()
+    rc = lib.dots_gemm_bf16(None, ctypes.c_longlong(8), None, ctypes.c_longlong(8), None, ctypes.c_longlong(8), 16, 16, 7, 0,
+                            None, None, ctypes.c_longlong(0), None)
+    assert rc == -1 and b"multiples of 8" in lib.dots_last_error()
+    rc = lib.dots_attn_varlen_fwd(None, ctypes.c_longlong(0), None, ctypes.c_longlong(0), None, ctypes.c_longlong(0), None,
+                                  ctypes.c_longlong(0), None, 1, 1, 12, 12, 64, 0, ctypes.c_float(1.0), None)
+    assert rc == -1 and b"head_dim" in lib.dots_last_error()
+    rc = lib.dots_rmsnorm(None, ctypes.c_longlong(8), None, None, ctypes.c_longlong(8), ctypes.c_longlong(4), 4100,
+                          ctypes.c_float(1e-6), None)
+    assert rc == -1

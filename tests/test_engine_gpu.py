@@ -10,11 +10,14 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# Tolerance for bf16 pre-sampling logits: max |engine - oracle| <= LOGIT_TOL * std(oracle logits).
-# Both sides round every Linear to bf16 (8 mantissa bits, 2^-9 relative per rounding); ~60 rounded
-# ops deep the observed spread between two *correct* bf16 implementations (HF-CUDA vs HF-CPU) is
-# ~1e-2 of the logit std, so 4e-2 separates rounding noise from real bugs (which show up as O(1)).
-LOGIT_TOL = 4e-2
+# Tolerances for bf16 pre-sampling logits, in units of std(oracle logits) (max over batch, step, vocab):
+#  * vs the reference HF forward in bf16 on the same GPU (T1): <= LOGIT_TOL_T1.  bf16 logits of
+#    magnitude 2-4 sigma are quantised in steps of ~0.03 sigma, so two correct bf16 pipelines differ by
+#    1-2 such steps at the worst element (measured: 0.034-0.041); real bugs show up as O(1).
+#  * vs the fp32 CPU oracle (T0): no worse than 1.5x what HF's own bf16 forward shows against T0
+#    (measured 0.029-0.039 for both), floor LOGIT_TOL_T0_FLOOR.
+LOGIT_TOL_T1 = 6e-2
+LOGIT_TOL_T0_FLOOR = 4e-2
 
 
 def _inputs(cfg, grids, n_text_front=5, n_text_back=7, seed=7):
@@ -114,11 +117,17 @@ def test_teacher_forced_logits_random(tiny):
     out = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N, forced_ids=new, return_logits=True)
     assert torch.equal(out.sequences[:, ids.shape[1]:].cpu(), new)                   # forcing took effect
     got = out.logits.float().cpu()
-    err = float((got - ref_logits).abs().max() / ref_logits.std())
-    assert err < LOGIT_TOL, err
+    sd = ref_logits.std()
+    ref16 = DotsOracle(cfg, ck, torch.bfloat16, DEV).teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()
+    err_t1 = float((got - ref16).abs().max() / sd)
+    err_t0 = float((got - ref_logits).abs().max() / sd)
+    hf_t0 = float((ref16 - ref_logits).abs().max() / sd)
+    print(f"logit err / sigma: engine-vs-HF-bf16 {err_t1:.4f}, engine-vs-fp32 {err_t0:.4f}, HF-bf16-vs-fp32 {hf_t0:.4f}")
+    assert err_t1 < LOGIT_TOL_T1, err_t1
+    assert err_t0 < max(1.5 * hf_t0, LOGIT_TOL_T0_FLOOR), (err_t0, hf_t0)
     # wherever the oracle's top-1 margin clears the tolerance, the engine's argmax must agree
     top2 = ref_logits.topk(2, -1).values
-    clear = (top2[..., 0] - top2[..., 1]) > 2 * LOGIT_TOL * ref_logits.std()
+    clear = (top2[..., 0] - top2[..., 1]) > 2 * LOGIT_TOL_T1 * sd
     assert clear.float().mean() > 0.3
     assert torch.equal(got.argmax(-1)[clear], ref_logits.argmax(-1)[clear])
 
