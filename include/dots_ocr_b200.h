@@ -71,6 +71,14 @@ DOTS_API int dots_attn_varlen_fwd(const void* q, long long q_stride, const void*
                          int max_seqlen, int n_q_heads, int n_kv_heads, int head_dim, int causal,
                          float softmax_scale, void* stream);
 
+/* Same contract on the tcgen05 tensor cores (S = QK^T and O += PV accumulate in TMEM, K/V tiles arrive by TMA,
+ * two 128-row query tiles per CTA ping-pong between the tensor pipe and the softmax warps).  total_tokens =
+ * cu_seqlens[n_seqs] (rows of the q/k/v/out buffers; bounds the TMA maps).  Token strides % 8 == 0. */
+DOTS_API int dots_attn_varlen_fwd_tc(const void* q, long long q_stride, const void* k, long long k_stride, const void* v,
+                            long long v_stride, void* out, long long o_stride, const int* cu_seqlens, int n_seqs,
+                            int max_seqlen, long long total_tokens, int n_q_heads, int n_kv_heads, int head_dim,
+                            int causal, float softmax_scale, void* stream);
+
 /* One-token-per-sequence attention over the KV cache [batch, n_kv_heads, ctx_max, 128]
  * (replaces DynamicCache + sdpa/flash decode, transformers/cache_utils.py:102-120, [Q]:227-241).
  * ctx_len[b] = number of visible keys (current token's key already appended).

@@ -80,10 +80,15 @@ def main():
             out = torch.empty((T, hq * 128), device=DEV, dtype=torch.bfloat16)
             cu = torch.arange(0, nseq + 1, device=DEV, dtype=torch.int32) * L
             q, k, v = qkv[:, : hq * 128], qkv[:, hq * 128:(hq + hkv) * 128], qkv[:, (hq + hkv) * 128:]
-            ms = timeit(lambda: ops.attn_varlen(q, k, v, out, cu, L, hq, hkv, causal, 128 ** -0.5))
             fl = 4.0 * L * L * 128 * hq * nseq * (0.5 if causal else 1.0)
-            print(json.dumps(dict(k="attn", L=L, nseq=nseq, hq=hq, hkv=hkv, causal=causal, ms=round(ms, 4),
-                                  tflops=round(fl / ms / 1e9, 1))), flush=True)
+            for impl in ("mma", "tc"):
+                try:
+                    ms = timeit(lambda: ops.attn_varlen(q, k, v, out, cu, L, hq, hkv, causal, 128 ** -0.5, impl=impl))
+                except Exception as e:
+                    print(json.dumps(dict(k="attn", impl=impl, error=repr(e)[:200])), flush=True)
+                    continue
+                print(json.dumps(dict(k="attn", impl=impl, L=L, nseq=nseq, hq=hq, hkv=hkv, causal=causal, ms=round(ms, 4),
+                                      tflops=round(fl / ms / 1e9, 1))), flush=True)
     if "decode" in only:
         for (B, ctx, splits) in [(64, 1881, 3), (64, 1881, 1), (64, 1881, 6), (1, 1881, 16), (32, 6200, 6)]:
             hq, hkv = 12, 2
