@@ -370,6 +370,31 @@ __global__ void __launch_bounds__(1024) argmax_advance_kernel(const bf16* __rest
 }
 
 // ------------------------------------------------------------------ decode-step finalize kernels
+// acc[0..7] += sum over splits of 8 consecutive fp32 at p0 + s * sstride, in split order (deterministic), with four
+// independent 32-byte loads in flight per thread.
+__device__ __forceinline__ void sum_splits8(const float* __restrict__ p0, long long sstride, int splits, float (&acc)[8]) {
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+        float4 a[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4* ps = reinterpret_cast<const float4*>(p0 + (s + u) * sstride);
+            a[u] = ps[0]; d[u] = ps[1];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+            acc[4] += d[u].x; acc[5] += d[u].y; acc[6] += d[u].z; acc[7] += d[u].w;
+        }
+    }
+    for (; s < splits; ++s) {
+        const float4* ps = reinterpret_cast<const float4*>(p0 + s * sstride);
+        const float4 a = ps[0], d = ps[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += d.x; acc[5] += d.y; acc[6] += d.z; acc[7] += d.w;
+    }
+}
+
 // All take split-K partial sums [splits][B][N] fp32 from dots_gemm_skinny_bf16 and reduce them in a
 // fixed order (deterministic), then apply the HF rounding points.
 
@@ -413,49 +438,44 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
     }
 }
 
-// x = bf16(sum partial); resid = bf16(resid + x); normed = RMSNorm(resid) * w      (one warp per sequence)
+// x = bf16(sum partial); resid = bf16(resid + x); normed = RMSNorm(resid) * w
+// One CTA per sequence, one 8-column chunk per thread (H / 8 <= 256 threads): the split-K partials of a row are
+// [splits] strided reads of 32 B per thread, all independent, so the whole reduction is one round of loads.
 __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const float* __restrict__ partial, int splits,
                                                                       bf16* __restrict__ resid, const bf16* __restrict__ w,
                                                                       bf16* __restrict__ normed, int B, int H, float eps) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 8 + warp;
-    if (b >= B) return;
+    __shared__ float s_part[8];
+    const int b = blockIdx.x;
+    const int c = threadIdx.x;
     const int nchunks = H >> 3;
-    float vals[NORM_MAX_CHUNKS][8];
+    const bool live = c < nchunks;
+    float x[8];
     float ss = 0.f;
+    if (live) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        sum_splits8(partial + (long long)b * H + c * 8, (long long)B * H, splits, acc);
+        float rr[8];
+        unpack8(reinterpret_cast<const uint4*>(resid + (long long)b * H)[c], rr);
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
-        const int c = lane + i * 32;
-        if (c < nchunks) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int s = 0; s < splits; ++s) {
-                const float4* ps = reinterpret_cast<const float4*>(partial + ((long long)s * B + b) * H + c * 8);
-                const float4 a = ps[0], d = ps[1];
-                acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-                acc[4] += d.x; acc[5] += d.y; acc[6] += d.z; acc[7] += d.w;
-            }
-            float rr[8];
-            unpack8(reinterpret_cast<const uint4*>(resid + (long long)b * H)[c], rr);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float x = bf16_round(bf16_round(acc[j]) + rr[j]);
-                vals[i][j] = x;
-                ss += x * x;
-            }
-            reinterpret_cast<uint4*>(resid + (long long)b * H)[c] = pack8(vals[i]);
+        for (int j = 0; j < 8; ++j) {
+            x[j] = bf16_round(bf16_round(acc[j]) + rr[j]);
+            ss += x[j] * x[j];
         }
+        reinterpret_cast<uint4*>(resid + (long long)b * H)[c] = pack8(x);
     }
-    const float r = rsqrtf(warp_sum(ss) / (float)H + eps);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) tot += s_part[i];
+    const float r = rsqrtf(tot / (float)H + eps);
+    if (live) {
+        float g[8], f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_CHUNKS; ++i) {
-        const int c = lane + i * 32;
-        if (c < nchunks) {
-            float g[8], f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = bf16_round(vals[i][j] * r) * g[j];
-            reinterpret_cast<uint4*>(normed + (long long)b * H)[c] = pack8(f);
-        }
+        for (int j = 0; j < 8; ++j) f[j] = bf16_round(x[j] * r) * g[j];
+        reinterpret_cast<uint4*>(normed + (long long)b * H)[c] = pack8(f);
     }
 }
 
@@ -473,13 +493,8 @@ __global__ void decode_qkv_rope_append_kernel(const float* __restrict__ partial,
     float x1[8], x2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { x1[j] = 0.f; x2[j] = 0.f; }
-    for (int s = 0; s < splits; ++s) {
-        const float* ps = partial + ((long long)s * B + b) * N + col;
-        const float4 a = *reinterpret_cast<const float4*>(ps), d = *reinterpret_cast<const float4*>(ps + 4);
-        const float4 e = *reinterpret_cast<const float4*>(ps + 64), f = *reinterpret_cast<const float4*>(ps + 68);
-        x1[0] += a.x; x1[1] += a.y; x1[2] += a.z; x1[3] += a.w; x1[4] += d.x; x1[5] += d.y; x1[6] += d.z; x1[7] += d.w;
-        x2[0] += e.x; x2[1] += e.y; x2[2] += e.z; x2[3] += e.w; x2[4] += f.x; x2[5] += f.y; x2[6] += f.z; x2[7] += f.w;
-    }
+    sum_splits8(partial + (long long)b * N + col, (long long)B * N, splits, x1);
+    sum_splits8(partial + (long long)b * N + col + 64, (long long)B * N, splits, x2);
     float b1[8], b2[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(bias + col)), b1);
     unpack8(__ldg(reinterpret_cast<const uint4*>(bias + col + 64)), b2);
@@ -512,13 +527,8 @@ __global__ void decode_swiglu_kernel(const float* __restrict__ partial, int spli
     float gsum[8], usum[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { gsum[j] = 0.f; usum[j] = 0.f; }
-    for (int s = 0; s < splits; ++s) {
-        const float* ps = partial + ((long long)s * B + b) * (2LL * I) + gcol;
-        const float4 a = *reinterpret_cast<const float4*>(ps), d = *reinterpret_cast<const float4*>(ps + 4);
-        const float4 e = *reinterpret_cast<const float4*>(ps + 128), f = *reinterpret_cast<const float4*>(ps + 132);
-        gsum[0] += a.x; gsum[1] += a.y; gsum[2] += a.z; gsum[3] += a.w; gsum[4] += d.x; gsum[5] += d.y; gsum[6] += d.z; gsum[7] += d.w;
-        usum[0] += e.x; usum[1] += e.y; usum[2] += e.z; usum[3] += e.w; usum[4] += f.x; usum[5] += f.y; usum[6] += f.z; usum[7] += f.w;
-    }
+    sum_splits8(partial + (long long)b * (2LL * I) + gcol, (long long)B * 2LL * I, splits, gsum);
+    sum_splits8(partial + (long long)b * (2LL * I) + gcol + 128, (long long)B * 2LL * I, splits, usum);
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -639,7 +649,8 @@ extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table
 extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed, int batch,
                                             int H, float eps, void* stream) {
     DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
-    decode_residual_rmsnorm_kernel<<<(batch + 7) / 8, 256, 0, ST(stream)>>>(partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch,
+    const int threads = ((H / 8) + 31) / 32 * 32;
+    decode_residual_rmsnorm_kernel<<<batch, threads, 0, ST(stream)>>>(partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch,
                                                                            H, eps);
     DOTS_LAUNCH_CHECK();
     return 0;

@@ -225,17 +225,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
             } else {
+                // Two 32-column chunks per iteration: both TMEM loads and (for the residual epilogue) all eight 16-byte
+                // residual loads are issued before the first use, so one iteration pays one memory latency, not two.
+                static_assert(BLOCK_N % 64 == 0, "generic epilogue walks the tile in 64-column steps");
                 bf16* out = reinterpret_cast<bf16*>(p.out);
+                const bool row_ok = row < p.M;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, v);
+                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                    uint32_t v[2][32];
+                    tmem_ld_32x32b_x32(t_row + c * 32, v[0]);
+                    tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[1]);
+                    const int col0 = n_blk * BLOCK_N + c * 32;
+                    uint4 rres[2][4];
+                    if constexpr (EPI == DOTS_EPI_RESIDUAL) {
+                        const bf16* rsrc = p.res + (long long)row * p.ldr + col0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                rres[h][q] = (row_ok && col0 + h * 32 + q * 8 + 8 <= p.N)
+                                                 ? *reinterpret_cast<const uint4*>(rsrc + h * 32 + q * 8) : make_uint4(0, 0, 0, 0);
+                    }
                     tmem_ld_wait();
-                    const int col = n_blk * BLOCK_N + c * 32;
-                    if (row < p.M && col < p.N) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = col0 + h * 32;
+                        if (!(row_ok && col < p.N)) continue;
                         float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[h][j]);
                         if constexpr (EPI == DOTS_EPI_BIAS || EPI == DOTS_EPI_BIAS_GELU) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -253,20 +271,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(bf16_round(f[j]));
                         }
                         if constexpr (EPI == DOTS_EPI_RESIDUAL) {
-                            const bf16* rsrc = p.res + (long long)row * p.ldr + col;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                if (col + q * 8 + 8 <= p.N) {
-                                    uint4 r = *reinterpret_cast<const uint4*>(rsrc + q * 8);
-                                    f[q * 8 + 0] = bf16_round(f[q * 8 + 0]) + bf16_lo(r.x);
-                                    f[q * 8 + 1] = bf16_round(f[q * 8 + 1]) + bf16_hi(r.x);
-                                    f[q * 8 + 2] = bf16_round(f[q * 8 + 2]) + bf16_lo(r.y);
-                                    f[q * 8 + 3] = bf16_round(f[q * 8 + 3]) + bf16_hi(r.y);
-                                    f[q * 8 + 4] = bf16_round(f[q * 8 + 4]) + bf16_lo(r.z);
-                                    f[q * 8 + 5] = bf16_round(f[q * 8 + 5]) + bf16_hi(r.z);
-                                    f[q * 8 + 6] = bf16_round(f[q * 8 + 6]) + bf16_lo(r.w);
-                                    f[q * 8 + 7] = bf16_round(f[q * 8 + 7]) + bf16_hi(r.w);
-                                }
+                                const uint4 r = rres[h][q];
+                                f[q * 8 + 0] = bf16_round(f[q * 8 + 0]) + bf16_lo(r.x);
+                                f[q * 8 + 1] = bf16_round(f[q * 8 + 1]) + bf16_hi(r.x);
+                                f[q * 8 + 2] = bf16_round(f[q * 8 + 2]) + bf16_lo(r.y);
+                                f[q * 8 + 3] = bf16_round(f[q * 8 + 3]) + bf16_hi(r.y);
+                                f[q * 8 + 4] = bf16_round(f[q * 8 + 4]) + bf16_lo(r.z);
+                                f[q * 8 + 5] = bf16_round(f[q * 8 + 5]) + bf16_hi(r.z);
+                                f[q * 8 + 6] = bf16_round(f[q * 8 + 6]) + bf16_lo(r.w);
+                                f[q * 8 + 7] = bf16_round(f[q * 8 + 7]) + bf16_hi(r.w);
                             }
                         }
                         bf16* dst = out + (long long)row * p.ldo + col;

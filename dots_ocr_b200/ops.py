@@ -105,7 +105,7 @@ def pick_splits(n_tiles: int, num_kb: int, sms: int = 148) -> int:
     return best
 
 
-ATTN_IMPL = "mma"      # "tc": tcgen05/TMEM kernel, "mma": mma.sync kernel
+ATTN_IMPL = "tc"       # "tc": tcgen05/TMEM kernel (product path); "mma": mma.sync kernel (kept as the cross-check)
 
 
 def attn_varlen(q, k, v, out, cu_seqlens, max_seqlen: int, n_q_heads: int, n_kv_heads: int, causal: bool,
