@@ -217,6 +217,8 @@ def run_gpu(args):
     from dots_ocr_b200.engine import Engine
     if args.attn_impl:
         ops.ATTN_IMPL = args.attn_impl
+    if args.no_pdl:
+        ops.set_pdl(False)
     cfg = config.PRESETS[args.preset]()
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev)
     eng = Engine(cfg, ck, dev)
@@ -353,6 +355,7 @@ def main():
     ap.add_argument("--preset", default="full")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
     ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "mma"])
     args = ap.parse_args()
     if args.impl == "reference":

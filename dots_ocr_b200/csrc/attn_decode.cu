@@ -7,6 +7,7 @@
 // Partial (m, l, O) triples are merged in shared memory, then across splits by a small combine
 // kernel.  This kernel is HBM-bound: bytes = 2 * ctx * 256 B per (sequence, kv head).
 #include "common.h"
+#include "ptx.cuh"
 #include "mma_sm80.cuh"
 #include "../../include/dots_ocr_b200.h"
 
@@ -46,6 +47,8 @@ __device__ __forceinline__ void dec_load_tile(uint8_t* dst, const bf16* gsrc_row
 
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const DecParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sQ = smem;
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -213,6 +216,8 @@ attn_decode_kernel(const DecParams p) {
 __global__ void __launch_bounds__(DEC_D)
 attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ out,
                            int n_splits) {
+    pdl_wait();
+    pdl_launch_dependents();
     const long long bh = blockIdx.x;          // b * n_q_heads + head
     const int c = threadIdx.x;
     float m = -INFINITY;
@@ -250,11 +255,9 @@ extern "C" int dots_attn_decode(const void* q, const void* k_cache, const void* 
         configured = true;
     }
     dim3 grid(n_splits, n_kv_heads, batch);
-    attn_decode_kernel<<<grid, DEC_THREADS, DEC_SMEM, st>>>(p);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, p));
     if (n_splits > 1) {
-        attn_decode_combine_kernel<<<batch * n_q_heads, DEC_D, 0, st>>>(part_o, part_ml, (bf16*)out, n_splits);
-        DOTS_LAUNCH_CHECK();
+        DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, part_o, part_ml, (bf16*)out, n_splits));
     }
     return 0;
 }

@@ -7,6 +7,7 @@
 namespace dots {
 
 static thread_local char g_err[1024] = "";
+int g_pdl = 1;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -98,6 +99,11 @@ extern "C" int dots_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (sm_count) *sm_count = prop.multiProcessorCount;
     if (cc_major) *cc_major = prop.major;
     if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+extern "C" int dots_set_pdl(int enable) {
+    dots::g_pdl = enable ? 1 : 0;
     return 0;
 }
 

@@ -40,6 +40,22 @@ int num_sms();
         }                                                                                  \
     } while (0)
 
+// Programmatic dependent launch (PDL): kernels launched through launch_ex(..., pdl=true) may start while their stream
+// predecessor is still running; they call pdl_wait() (ptx.cuh) before touching anything a predecessor writes.
+// dots_set_pdl(0) turns the attribute off globally (plain stream serialisation).
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // 2-D bf16 row-major tensor [rows, cols] with row pitch ld (elements) -> TMA map with a
 // {64 x box_rows} box and 128-byte swizzle.  Returns 0 on success.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,

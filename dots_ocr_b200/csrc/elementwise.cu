@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // (TMA needs a 16-byte row pitch; 588 * 2 B is not).  HF: hidden_states.to(bf16).
 __global__ void cast_pad_kernel(const void* __restrict__ in, int in_is_bf16, long long rows, int cols, bf16* __restrict__ out,
                                 int ldo) {
+    pdl_wait();
+    pdl_launch_dependents();
     const long long total = rows * (ldo / 2);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / (ldo / 2);
@@ -52,6 +54,8 @@ constexpr int NORM_MAX_CHUNKS = 8;     // per lane; cols <= 8 * 32 * 8 = 2048 on
 
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
                                                       bf16* __restrict__ out, long long ldo, long long rows, int cols, float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = blockIdx.x * 8LL + warp;
     if (row >= rows) return;
@@ -93,6 +97,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
                                                         const bf16* __restrict__ b, bf16* __restrict__ out, long long ldo,
                                                         long long rows, int cols, float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = blockIdx.x * 8LL + warp;
     if (row >= rows) return;
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 __global__ void vit_rope_table_kernel(const int* __restrict__ cu, const int* __restrict__ grid_hw, int n_img,
                                       const float* __restrict__ inv_freq, int half, int merge, float* __restrict__ cos_t,
                                       float* __restrict__ sin_t, int total_tokens) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int dim = 2 * half;
     if (idx >= total_tokens * dim) return;
@@ -171,6 +179,8 @@ __global__ void vit_rope_table_kernel(const int* __restrict__ cu, const int* __r
 // one rounding (ApplyRotaryEmb, enable_fp32_compute=True).  One thread = 8 (x1, x2) pairs.
 __global__ void vit_rope_apply_kernel(bf16* __restrict__ qkv, long long ld, int S, int heads, const float* __restrict__ cos_t,
                                       const float* __restrict__ sin_t) {
+    pdl_wait();
+    pdl_launch_dependents();
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long total = (long long)S * heads * 2 * 8;
     if (idx >= total) return;
@@ -215,6 +225,8 @@ __device__ __forceinline__ void rope_bf16_8(const float (&x1)[8], const float (&
 __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int T, int nq, int nkv, const int* __restrict__ pos,
                                        const int* __restrict__ seq_of_tok, const float* __restrict__ inv_freq,
                                        bf16* __restrict__ kc, bf16* __restrict__ vc, long long ctx_max) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int units = (nq + 2 * nkv) * 8;           // 8 threads per head (each: 8 low + 8 high dims)
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)T * units) return;
@@ -247,6 +259,8 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int
 // slots[t] = rank of token t among image-pad tokens (masked_scatter order), or -1 for text tokens.
 __global__ void __launch_bounds__(1024) image_slots_kernel(const long long* __restrict__ ids, int T, long long image_token,
                                                            int* __restrict__ slots, int* __restrict__ count_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
     __shared__ int carry;
@@ -286,6 +300,8 @@ __global__ void __launch_bounds__(1024) image_slots_kernel(const long long* __re
 
 __global__ void embed_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ slots, const bf16* __restrict__ table,
                                      const bf16* __restrict__ img, bf16* __restrict__ out, int T, int H, long long vocab) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int chunks = H >> 3;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)T * chunks) return;
@@ -303,6 +319,8 @@ __global__ void embed_scatter_kernel(const long long* __restrict__ ids, const in
 
 __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long lds, const int* __restrict__ rows, bf16* __restrict__ out,
                                    long long ldo, int n, int cols) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int chunks = cols >> 3;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)n * chunks) return;
@@ -320,6 +338,8 @@ __global__ void __launch_bounds__(1024) argmax_advance_kernel(const bf16* __rest
                                                               int* __restrict__ ctx_len, int* __restrict__ finished,
                                                               long long eos_id, long long pad_id, const long long* __restrict__ forced,
                                                               long long forced_ld) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const bf16* row = logits + (long long)b * ldl;
     float best = -INFINITY;
@@ -402,6 +422,8 @@ __device__ __forceinline__ void sum_splits8(const float* __restrict__ p0, long l
 __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table,
                                                                    long long vocab, const bf16* __restrict__ w, bf16* __restrict__ resid,
                                                                    bf16* __restrict__ normed, int B, int H, float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
     if (b >= B) return;
@@ -444,6 +466,8 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
 __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const float* __restrict__ partial, int splits,
                                                                       bf16* __restrict__ resid, const bf16* __restrict__ w,
                                                                       bf16* __restrict__ normed, int B, int H, float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float s_part[8];
     const int b = blockIdx.x;
     const int c = threadIdx.x;
@@ -483,6 +507,8 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
 __global__ void decode_qkv_rope_append_kernel(const float* __restrict__ partial, int splits, const bf16* __restrict__ bias,
                                               const int* __restrict__ pos, const float* __restrict__ inv_freq, bf16* __restrict__ q_out,
                                               bf16* __restrict__ kc, bf16* __restrict__ vc, long long ctx_max, int B, int nq, int nkv) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int units = (nq + 2 * nkv) * 8;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * units) return;
@@ -518,6 +544,8 @@ __global__ void decode_qkv_rope_append_kernel(const float* __restrict__ partial,
 // act = bf16( bf16(silu(bf16 gate)) * bf16 up ), gate/up interleaved per 256-column block
 // ([128 gate | 128 up], the layout the prefill SWIGLU epilogue uses), partial [splits][B][2I].
 __global__ void decode_swiglu_kernel(const float* __restrict__ partial, int splits, bf16* __restrict__ act, int B, int I) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int chunks = I >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * chunks) return;
@@ -547,8 +575,7 @@ extern "C" int dots_cast_pad_bf16(const void* in, int in_is_bf16, long long rows
     DOTS_REQUIRE(rows > 0 && cols > 0 && ldo >= cols && ldo % 8 == 0, "dots_cast_pad_bf16: bad shape rows=%lld cols=%d ldo=%d", rows, cols, ldo);
     const long long total = rows * (ldo / 2);
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    cast_pad_kernel<<<blocks, 256, 0, ST(stream)>>>(in, in_is_bf16, rows, cols, (bf16*)out, ldo);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(cast_pad_kernel, dim3(blocks), dim3(256), (size_t)(0), ST(stream), true, in, in_is_bf16, rows, cols, (bf16*)out, ldo));
     return 0;
 }
 
@@ -556,8 +583,7 @@ extern "C" int dots_rmsnorm(const void* x, long long ldx, const void* w, void* o
                             float eps, void* stream) {
     DOTS_REQUIRE(rows > 0 && cols % 8 == 0 && cols <= NORM_MAX_CHUNKS * 256 && ldx % 8 == 0 && ldo % 8 == 0,
                  "dots_rmsnorm: need cols %% 8 == 0, cols <= 2048, 16-byte pitches (cols=%d)", cols);
-    rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)out, ldo, rows, cols, eps);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(rmsnorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), ST(stream), true, (const bf16*)x, ldx, (const bf16*)w, (bf16*)out, ldo, rows, cols, eps));
     return 0;
 }
 
@@ -565,9 +591,7 @@ extern "C" int dots_layernorm(const void* x, long long ldx, const void* w, const
                               long long rows, int cols, float eps, void* stream) {
     DOTS_REQUIRE(rows > 0 && cols % 8 == 0 && cols <= NORM_MAX_CHUNKS * 256 && ldx % 8 == 0 && ldo % 8 == 0,
                  "dots_layernorm: need cols %% 8 == 0, cols <= 2048, 16-byte pitches (cols=%d)", cols);
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)out, ldo,
-                                                                       rows, cols, eps);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(layernorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), ST(stream), true, (const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)out, ldo, rows, cols, eps));
     return 0;
 }
 
@@ -575,9 +599,7 @@ extern "C" int dots_vit_rope_table(const int* cu_seqlens, const int* grid_hw, in
                                    int merge, float* cos_t, float* sin_t, int total_tokens, void* stream) {
     DOTS_REQUIRE(n_img > 0 && total_tokens > 0 && half == 32 && merge > 0, "dots_vit_rope_table: bad args (half must be 32)");
     const long long n = (long long)total_tokens * 2 * half;
-    vit_rope_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(cu_seqlens, grid_hw, n_img, inv_freq, half, merge, cos_t, sin_t,
-                                                                             total_tokens);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(vit_rope_table_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), ST(stream), true, cu_seqlens, grid_hw, n_img, inv_freq, half, merge, cos_t, sin_t, total_tokens));
     return 0;
 }
 
@@ -585,8 +607,7 @@ extern "C" int dots_vit_rope_apply(void* qkv, long long ld, int S, int heads, in
                                    void* stream) {
     DOTS_REQUIRE(S > 0 && heads > 0 && head_dim == 128 && ld % 8 == 0, "dots_vit_rope_apply: head_dim must be 128, pitch %% 8 == 0");
     const long long n = (long long)S * heads * 2 * 8;
-    vit_rope_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((bf16*)qkv, ld, S, heads, cos_t, sin_t);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(vit_rope_apply_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), ST(stream), true, (bf16*)qkv, ld, S, heads, cos_t, sin_t));
     return 0;
 }
 
@@ -595,16 +616,13 @@ extern "C" int dots_llm_rope_kv_append(void* qkv, long long ld, int T, int n_q_h
                                        void* v_cache, long long ctx_max, void* stream) {
     DOTS_REQUIRE(T > 0 && head_dim == 128 && ld % 8 == 0, "dots_llm_rope_kv_append: head_dim must be 128");
     const long long n = (long long)T * (n_q_heads + 2 * n_kv_heads) * 8;
-    llm_rope_append_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((bf16*)qkv, ld, T, n_q_heads, n_kv_heads, positions,
-                                                                              seq_of_tok, inv_freq, (bf16*)k_cache, (bf16*)v_cache, ctx_max);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(llm_rope_append_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), ST(stream), true, (bf16*)qkv, ld, T, n_q_heads, n_kv_heads, positions, seq_of_tok, inv_freq, (bf16*)k_cache, (bf16*)v_cache, ctx_max));
     return 0;
 }
 
 extern "C" int dots_image_slots(const long long* ids, int T, long long image_token_id, int* slots, int* count_out, void* stream) {
     DOTS_REQUIRE(T > 0, "dots_image_slots: empty input");
-    image_slots_kernel<<<1, 1024, 0, ST(stream)>>>(ids, T, image_token_id, slots, count_out);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(image_slots_kernel, dim3(1), dim3(1024), (size_t)(0), ST(stream), true, ids, T, image_token_id, slots, count_out));
     return 0;
 }
 
@@ -612,9 +630,7 @@ extern "C" int dots_embed_scatter(const long long* ids, const int* slots, const 
                                   int T, int H, long long vocab, void* stream) {
     DOTS_REQUIRE(T > 0 && H % 8 == 0, "dots_embed_scatter: bad shape");
     const long long n = (long long)T * (H / 8);
-    embed_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(ids, slots, (const bf16*)table, (const bf16*)img_embeds, (bf16*)out,
-                                                                            T, H, vocab);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(embed_scatter_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), ST(stream), true, ids, slots, (const bf16*)table, (const bf16*)img_embeds, (bf16*)out, T, H, vocab));
     return 0;
 }
 
@@ -622,8 +638,7 @@ extern "C" int dots_gather_rows(const void* src, long long lds, const int* rows,
                                 void* stream) {
     DOTS_REQUIRE(n > 0 && cols % 8 == 0 && lds % 8 == 0 && ldo % 8 == 0, "dots_gather_rows: bad shape");
     const long long t = (long long)n * (cols / 8);
-    gather_rows_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>((const bf16*)src, lds, rows, (bf16*)out, ldo, n, cols);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(gather_rows_kernel, dim3((unsigned)((t + 255) / 256)), dim3(256), (size_t)(0), ST(stream), true, (const bf16*)src, lds, rows, (bf16*)out, ldo, n, cols));
     return 0;
 }
 
@@ -631,18 +646,14 @@ extern "C" int dots_argmax_advance(const void* logits, long long ldl, int batch,
                                    long long out_ld, int* step, int* pos, int* ctx_len, int* finished, long long eos_id,
                                    long long pad_id, const long long* forced_ids, long long forced_ld, void* stream) {
     DOTS_REQUIRE(batch > 0 && vocab % 8 == 0 && ldl % 8 == 0, "dots_argmax_advance: vocab and pitch must be multiples of 8");
-    argmax_advance_kernel<<<batch, 1024, 0, ST(stream)>>>((const bf16*)logits, ldl, vocab, next_ids, out_ids, out_ld, step, pos, ctx_len,
-                                                         finished, eos_id, pad_id, forced_ids, forced_ld);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(argmax_advance_kernel, dim3(batch), dim3(1024), (size_t)(0), ST(stream), true, (const bf16*)logits, ldl, vocab, next_ids, out_ids, out_ld, step, pos, ctx_len, finished, eos_id, pad_id, forced_ids, forced_ld));
     return 0;
 }
 
 extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
                                          void* normed, int batch, int H, float eps, void* stream) {
     DOTS_REQUIRE(batch > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_embed_rmsnorm: H %% 8, H <= 2048");
-    decode_embed_rmsnorm_kernel<<<(batch + 7) / 8, 256, 0, ST(stream)>>>(ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid,
-                                                                        (bf16*)normed, batch, H, eps);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(decode_embed_rmsnorm_kernel, dim3((batch + 7) / 8), dim3(256), (size_t)(0), ST(stream), true, ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid, (bf16*)normed, batch, H, eps));
     return 0;
 }
 
@@ -650,9 +661,7 @@ extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, vo
                                             int H, float eps, void* stream) {
     DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
     const int threads = ((H / 8) + 31) / 32 * 32;
-    decode_residual_rmsnorm_kernel<<<batch, threads, 0, ST(stream)>>>(partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch,
-                                                                           H, eps);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps));
     return 0;
 }
 
@@ -661,16 +670,13 @@ extern "C" int dots_decode_qkv_rope_append(const float* partial, int splits, con
                                            int n_kv_heads, int head_dim, void* stream) {
     DOTS_REQUIRE(batch > 0 && splits > 0 && head_dim == 128, "dots_decode_qkv_rope_append: head_dim must be 128");
     const int n = batch * (n_q_heads + 2 * n_kv_heads) * 8;
-    decode_qkv_rope_append_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(partial, splits, (const bf16*)bias, pos, inv_freq, (bf16*)q_out,
-                                                                          (bf16*)k_cache, (bf16*)v_cache, ctx_max, batch, n_q_heads, n_kv_heads);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(decode_qkv_rope_append_kernel, dim3((n + 127) / 128), dim3(128), (size_t)(0), ST(stream), true, partial, splits, (const bf16*)bias, pos, inv_freq, (bf16*)q_out, (bf16*)k_cache, (bf16*)v_cache, ctx_max, batch, n_q_heads, n_kv_heads));
     return 0;
 }
 
 extern "C" int dots_decode_swiglu(const float* partial, int splits, void* act, int batch, int inter, void* stream) {
     DOTS_REQUIRE(batch > 0 && splits > 0 && inter % 128 == 0, "dots_decode_swiglu: intermediate size must be a multiple of 128");
     const int n = batch * (inter / 8);
-    decode_swiglu_kernel<<<(n + 255) / 256, 256, 0, ST(stream)>>>(partial, splits, (bf16*)act, batch, inter);
-    DOTS_LAUNCH_CHECK();
+    DOTS_CHECK_CUDA(launch_ex(decode_swiglu_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), ST(stream), true, partial, splits, (bf16*)act, batch, inter));
     return 0;
 }

@@ -24,6 +24,7 @@ constexpr int GEMM_THREADS = 256;
 struct GemmParams {
     int M, N, K;                   // rows of A, rows of B, reduction length
     int m_blocks, n_blocks, splits, kb_per_split, num_k_blocks;
+    int static_is_b;               // which operand holds weights (never written by an in-flight kernel): 1 = B, 0 = A (swap-AB)
     void* out;
     long long ldo;
     const bf16* bias;
@@ -31,12 +32,18 @@ struct GemmParams {
     long long ldr;
 };
 
-template <int BLOCK_N>
+constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T; }
+
+template <int BLOCK_N, int EPI>
 struct GemmSmem {
+    static constexpr bool SWAP = epi_is_swap_ab(EPI);
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    // Decode (swap-AB) kernels keep the ring under half an SM's shared memory so that two CTAs -- usually of two
+    // consecutive kernels of the decode step, overlapped by programmatic dependent launch -- stream weights at once.
+    static constexpr int STAGES = SWAP ? (BLOCK_N >= 256 ? 2 : 4) : (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int MIN_CTAS = (SWAP && BLOCK_N <= 128) ? 2 : 1;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
     static constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
@@ -54,10 +61,10 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_b
 }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, GemmSmem<BLOCK_N, EPI>::MIN_CTAS)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-    using S = GemmSmem<BLOCK_N>;
+    using S = GemmSmem<BLOCK_N, EPI>;
     constexpr int STAGES = S::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,22 +104,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();        // the next kernel of the stream may begin its own prologue / weight prefetch
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // Weights never depend on a predecessor kernel: put the first ring-full of weight tiles in flight BEFORE
+            // waiting for the dependency, so HBM keeps streaming across the kernel boundary.
+            int pre = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                int m_blk, n_blk, split;
+                tile_coords(p, blockIdx.x, m_blk, n_blk, split);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
+                    mbar_expect_tx(&full_bar[pre], S::STAGE_BYTES);
+                    if (p.static_is_b) tma_load_2d(smem_b + pre * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[pre]);
+                    else tma_load_2d(smem_a + pre * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[pre]);
+                }
+            }
+            pdl_wait();
+            int issued = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk, split;
                 tile_coords(p, t, m_blk, n_blk, split);
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
-                    tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[stage]);
+                for (int kb = kb0; kb < kb1; ++kb, ++issued) {
+                    if (issued < pre) {
+                        // static half already in flight on this stage's barrier: add the dependent half
+                        if (p.static_is_b) tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
+                        else tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[stage]);
+                    } else {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
+                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[stage]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -152,6 +182,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        pdl_wait();                                          // residual / bias reads and all output writes follow the dependency
         const int wq = warp & 3;                             // TMEM lane quarter this warp may read
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -317,7 +348,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
 template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    using S = GemmSmem<BLOCK_N>;
+    using S = GemmSmem<BLOCK_N, EPI>;
     auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>;
     static bool configured = false;
     if (!configured) {
@@ -325,9 +356,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
         configured = true;
     }
     const int tiles = p.m_blocks * p.n_blocks * p.splits;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, p);
-    DOTS_LAUNCH_CHECK();
+    const int slots = num_sms() * S::MIN_CTAS;
+    const int grid = tiles < slots ? tiles : slots;
+    DOTS_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)S::TOTAL, stream, true, ta, tb, p));
     return 0;
 }
 
@@ -350,6 +381,7 @@ extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long 
     p.res = reinterpret_cast<const bf16*>(residual);
     p.ldr = ldr;
     p.splits = 1;
+    p.static_is_b = 1;             // W holds weights
     p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
     p.kb_per_split = p.num_k_blocks;
     p.m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
@@ -406,6 +438,7 @@ extern "C" int dots_gemm_skinny_bf16(const void* X, long long ldx, const void* W
     DOTS_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "dots_gemm_skinny_bf16: K and pitches must be multiples of 8");
     DOTS_REQUIRE((partial != nullptr) != (out_bf16 != nullptr), "dots_gemm_skinny_bf16: pass exactly one of partial / out_bf16");
     GemmParams p{};
+    p.static_is_b = 0;     // swap-AB: the A operand holds the weights
     p.M = N;               // A operand = weights: rows are output features
     p.N = batch;           // B operand = activations
     p.K = K;

@@ -169,6 +169,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// No-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization.
+// pdl_wait(): every prerequisite grid has completed and its writes are visible.  Anything executed before it may only
+// touch memory no in-flight kernel writes (weights, this CTA's shared memory, TMEM).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

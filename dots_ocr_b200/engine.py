@@ -345,12 +345,19 @@ class Engine:
                 self._decode_step(st)                   # eager once (also warms every kernel variant)
                 done = 1
                 if n_steps > 1:
-                    g = ops.Graph()
                     cap = torch.cuda.Stream(device=dev)
                     cap.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(cap):
-                        with g:
-                            self._decode_step(st)
+                        try:
+                            g = ops.Graph()
+                            with g:
+                                self._decode_step(st)
+                        except RuntimeError:
+                            # a driver that cannot capture programmatic-dependent-launch edges: plain stream order
+                            ops.set_pdl(False)
+                            g = ops.Graph()
+                            with g:
+                                self._decode_step(st)
                         # capture does not execute: replay for every remaining step
                         for _ in range(n_steps - 1):
                             g.launch()

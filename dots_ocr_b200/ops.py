@@ -276,6 +276,11 @@ def decode_swiglu(partial, splits, act):
     _lib.check(rc, "dots_decode_swiglu")
 
 
+def set_pdl(enable: bool) -> None:
+    """Programmatic dependent launch between consecutive kernels (default on)."""
+    _lib.check(_lib.load().dots_set_pdl(int(bool(enable))), "dots_set_pdl")
+
+
 class Graph:
     """Capture the C-ABI launches issued inside the ``with`` block on the current stream."""
 

@@ -43,6 +43,10 @@ DOTS_API const char* dots_last_error(void);
 DOTS_API int dots_abi_version(void);
 DOTS_API int dots_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Programmatic dependent launch between consecutive kernels of a stream (default on): weight prefetch, barrier
+ * setup and TMEM allocation of kernel N+1 overlap the tail of kernel N.  0 = plain stream order. */
+DOTS_API int dots_set_pdl(int enable);
+
 /* ---- dense contractions (tcgen05 / TMEM / TMA) -------------------------------------------- */
 
 /* out[M, N(/2)] = epilogue(A[M, K] * W[N, K]^T).  Replaces every nn.Linear / Conv2d-as-GEMM on the

@@ -145,3 +145,26 @@ def test_eos_and_pad(tiny):
     out = eng.generate(ids, max_new_tokens=8, eos_token_id=eos, pad_token_id=0).sequences[:, 4:]
     assert out[0, :3].tolist() == chain[1:4] and out[0, 3:].tolist() == [0] * 5
     assert (out[1] != 0).all()
+
+
+def test_pdl_on_off_identical(tiny):
+    """Programmatic dependent launch only changes when kernels start, never what they compute."""
+    from dots_ocr_b200 import ops
+    cfg, d = tiny
+    ck, eng = d["random"]
+    pv, grid, rows = _inputs(cfg, [(1, 8, 8), (1, 8, 12)], n_text_back=11)
+    T = max(r.numel() for r in rows)
+    ids = torch.zeros((2, T), dtype=torch.long)
+    mask = torch.zeros((2, T), dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, T - r.numel():] = r
+        mask[i, T - r.numel():] = 1
+    outs = []
+    try:
+        for flag in (False, True, True):
+            ops.set_pdl(flag)
+            o = eng.generate(ids, attention_mask=mask, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=40)
+            outs.append(o.sequences.cpu())
+    finally:
+        ops.set_pdl(True)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
