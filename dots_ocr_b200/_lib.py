@@ -11,7 +11,8 @@ import re
 from typing import Dict, List
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdots_ocr_b200.so")
+# DOTS_B200_LIB selects an alternative build of the same ABI (kernel-tuning A/B runs); the default is the in-tree library.
+LIB_PATH = os.environ.get("DOTS_B200_LIB") or os.path.join(HERE, "libdots_ocr_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "dots_ocr_b200.h")
 
 _lib = None

@@ -1,19 +1,21 @@
 // Variable-length fused attention forward on the 5th-gen tensor cores (head_dim 128).
 //
-// One CTA owns TWO 128-row query tiles (A and B) of one (sequence, head) and ping-pongs them so the
-// tensor pipe works on one tile while the other tile's softmax runs (FA4-style schedule):
+// One CTA owns TWO 128-row query tiles ("chains" 0 and 1) of one (sequence, head).  Keys/values arrive in 64-key tiles.
+// Per chain the score tile S is DOUBLE-BUFFERED in TMEM, so S(j+1) = Q K_{j+1}^T is computed while the softmax warps
+// still work on S(j); the only true dependency left on the tensor pipe is P(j) -> O += P(j) V_j:
 //
-//   warp 0        TMA producer: Q_A, Q_B once; K_j / V_j tiles (128 keys) through mbarrier rings
-//   warp 1        tcgen05.mma issuer:  S_t = Q_t K_j^T  (SS: both operands in shared memory)
-//                                      O_t += P_t V_j   (TS: P read from TMEM, V MN-major in shared memory)
-//   warps 4-7     softmax warpgroup for tile A  (thread = query row = TMEM lane)
-//   warps 8-11    softmax warpgroup for tile B
+//   warp 0        TMA producer: Q_0, Q_1 once; K_j / V_j tiles (64 keys) through 4-deep mbarrier rings
+//   warp 1        tcgen05.mma issuer:  S_t(j) = Q_t K_j^T   (SS, 128x64x16 x 8)
+//                                      O_t  += P_t(j) V_j   (TS: P read from TMEM, V MN-major in smem, 128x128x16 x 4)
+//                 program order per chain:  S(0) S(1) | wait P(j): PV(j), S(j+2) | ...
+//   warps 4-7     softmax warpgroup of chain 0  (thread = query row = TMEM lane)
+//   warps 8-11    softmax warpgroup of chain 1
 //
-// TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512); P_t (bf16 pairs) overwrites
-// the first 64 columns of S_t.  Softmax is fp32 with exp2 and a pre-scaled log2(e); the running max is only
-// advanced when it grows by more than 2^8 (lazy rescale), so O in TMEM is rarely touched by the softmax warps.
-// P is rounded to bf16 before P*V, the row sum is accumulated from the unrounded fp32 values
-// (flash_attention_2's rounding points).
+// TMEM (512 columns): chain t at t*256: S buffer 0 [0,64)  S buffer 1 [64,128)  O [128,256).  P(j) (bf16 pairs) overwrites
+// the first 32 columns of the S buffer it came from.  Softmax is fp32 in the exp2 domain with packed fp32x2 arithmetic;
+// the running max only advances when it grows by more than 2^8 (lazy rescale), so O in TMEM is rarely touched by the
+// softmax warps (and when it is, they first wait for P(j-1) V to retire).  P is rounded to bf16 before P*V, the row sum
+// accumulates the unrounded fp32 values (flash_attention_2's rounding points).
 //
 // SURVEY.md §8a rows a10 (ViT, bidirectional, one segment per image) and a19 (LLM prefill, causal GQA).
 #include "common.h"
@@ -24,12 +26,13 @@ namespace dots {
 
 constexpr int FA_D = 128;
 constexpr int FA_BM = 128;          // rows per query tile (two tiles per CTA)
-constexpr int FA_BN = 128;          // keys per KV tile
+constexpr int FA_BN = 64;           // keys per KV tile
 constexpr int FA_THREADS = 384;
-constexpr int FA_TILE_BYTES = 128 * 128 * 2;        // 32 KB: one [128 x 128] bf16 tile = two 16-KB swizzle boxes
-constexpr int FA_KSTAGES = 3;
-constexpr int FA_VSTAGES = 2;
-constexpr int FA_SMEM = (2 + FA_KSTAGES + FA_VSTAGES) * FA_TILE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+constexpr int FA_QTILE_BYTES = FA_BM * FA_D * 2;     // 32 KB = two [128 x 64] swizzle boxes
+constexpr int FA_KVTILE_BYTES = FA_BN * FA_D * 2;    // 16 KB = two [64 x 64] swizzle boxes
+constexpr int FA_KSTAGES = 4;
+constexpr int FA_VSTAGES = 4;
+constexpr int FA_SMEM = 2 * FA_QTILE_BYTES + (FA_KSTAGES + FA_VSTAGES) * FA_KVTILE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
 
 struct FaParams {
     const int* cu;
@@ -68,25 +71,51 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
+// exp2 of two packed fp32 values on the FMA/ALU pipes (no MUFU): round-to-nearest range reduction with the 1.5*2^23
+// magic constant, a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the
+// bf16 rounding applied to P), and the integer part added straight into the exponent field.  The softmax warps run
+// one pair in four through this path so the MUFU pipe (16 ex2 / clk / SM) stops being the co-bottleneck of the
+// tensor pipe -- the FlashAttention-4 trick.
+__device__ __forceinline__ void ex2_poly_f32x2(uint64_t x2, float& p0, float& p1) {
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t t = fadd_f32x2(xc, pack_f32x2(12582912.f, 12582912.f));
+    const uint64_t n = fadd_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
+    const uint64_t f = ffma_f32x2(n, pack_f32x2(-1.f, -1.f), xc);
+    uint64_t q = ffma_f32x2(f, pack_f32x2(0.055171459913253784f, 0.055171459913253784f), pack_f32x2(0.2426108568906784f, 0.2426108568906784f));
+    q = ffma_f32x2(q, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+    q = ffma_f32x2(q, f, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(q, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+#ifndef FA_EMU_MASK
+#define FA_EMU_MASK 0u               // bit i set: packed pair i of the 32 pairs of a row takes the polynomial path
+#endif
+
 template <bool CAUSAL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const FaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                         // [2 tiles][2 boxes][128 rows][128 B]
-    uint8_t* sK = sQ + 2 * FA_TILE_BYTES;                       // [KSTAGES]
-    uint8_t* sV = sK + FA_KSTAGES * FA_TILE_BYTES;              // [VSTAGES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_VSTAGES * FA_TILE_BYTES);
+    uint8_t* sQ = smem;                                         // [2 chains][2 boxes][128 rows][128 B]
+    uint8_t* sK = sQ + 2 * FA_QTILE_BYTES;                      // [KSTAGES][2 boxes][64 rows][128 B]
+    uint8_t* sV = sK + FA_KSTAGES * FA_KVTILE_BYTES;            // [VSTAGES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_VSTAGES * FA_KVTILE_BYTES);
     uint64_t* q_full = bars;                    // [1]
     uint64_t* k_full = bars + 1;                // [KSTAGES]
     uint64_t* k_empty = k_full + FA_KSTAGES;    // [KSTAGES]
     uint64_t* v_full = k_empty + FA_KSTAGES;    // [VSTAGES]
     uint64_t* v_empty = v_full + FA_VSTAGES;    // [VSTAGES]
-    uint64_t* s_full = v_empty + FA_VSTAGES;    // [2]   MMA -> softmax: S_t ready
-    uint64_t* p_full = s_full + 2;              // [2]   softmax -> MMA: P_t written (and O_t rescaled)
-    uint64_t* o_done = p_full + 2;              // [2]   MMA -> softmax: last P*V of tile t retired
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+    uint64_t* s_full = v_empty + FA_VSTAGES;    // [2 chains][2 buffers]  MMA -> softmax: S_t(j) ready in buffer j&1
+    uint64_t* p_full = s_full + 4;              // [2][2]                 softmax -> MMA: P_t(j) written over buffer j&1
+    uint64_t* pv_done = p_full + 4;             // [2][2]                 MMA -> softmax: O_t += P_t(j) V_j retired
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 4);
 
     const int seq = blockIdx.z, head = blockIdx.y;
     const int tok0 = p.cu[seq];
@@ -104,9 +133,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int i = 0; i < FA_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-        for (int i = 0; i < FA_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_done[i], 1); }
+        for (int i = 0; i < FA_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }   // released by both issuing warps
+        for (int i = 0; i < FA_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -116,136 +145,168 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    // The CTA allocates all 512 TMEM columns, so the allocation starts at column 0 / lane 0.  Using the literal keeps every
+    // tcgen05.mma operand in uniform registers: the single issuing thread spends ~10 instructions per MMA instead of ~45
+    // (per-MMA broadcast loops on a non-uniform TMEM address), which matters when one 128x64x16 MMA is only 32 clocks.
+    if (*tmem_ptr != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
 
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // warpgroup 0 hands its registers to the softmax warpgroups
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");   // 128 x (168 - 96) released >= 256 x (200 - 168) acquired
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            mbar_expect_tx(q_full, 2 * FA_TILE_BYTES);
+            mbar_expect_tx(q_full, 2 * FA_QTILE_BYTES);
 #pragma unroll
             for (int t = 0; t < 2; ++t)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    tma_load_2d(sQ + t * FA_TILE_BYTES + h * (FA_TILE_BYTES / 2), &tm_q, head * FA_D + h * 64,
+                    tma_load_2d(sQ + t * FA_QTILE_BYTES + h * (FA_QTILE_BYTES / 2), &tm_q, head * FA_D + h * 64,
                                 tok0 + q0 + t * FA_BM, q_full);
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
             for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&k_empty[ks], kph ^ 1);
-                mbar_expect_tx(&k_full[ks], FA_TILE_BYTES);
+                const int ks = j % FA_KSTAGES, vs = j % FA_VSTAGES;
+                mbar_wait(&k_empty[ks], ((j / FA_KSTAGES) & 1) ^ 1);
+                mbar_expect_tx(&k_full[ks], FA_KVTILE_BYTES);
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    tma_load_2d(sK + ks * FA_TILE_BYTES + h * (FA_TILE_BYTES / 2), &tm_k, kvh * FA_D + h * 64, tok0 + j * FA_BN,
+                    tma_load_2d(sK + ks * FA_KVTILE_BYTES + h * (FA_KVTILE_BYTES / 2), &tm_k, kvh * FA_D + h * 64, tok0 + j * FA_BN,
                                 &k_full[ks]);
-                if (++ks == FA_KSTAGES) { ks = 0; kph ^= 1; }
-                mbar_wait(&v_empty[vs], vph ^ 1);
-                mbar_expect_tx(&v_full[vs], FA_TILE_BYTES);
+                mbar_wait(&v_empty[vs], ((j / FA_VSTAGES) & 1) ^ 1);
+                mbar_expect_tx(&v_full[vs], FA_KVTILE_BYTES);
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    tma_load_2d(sV + vs * FA_TILE_BYTES + h * (FA_TILE_BYTES / 2), &tm_v, kvh * FA_D + h * 64, tok0 + j * FA_BN,
+                    tma_load_2d(sV + vs * FA_KVTILE_BYTES + h * (FA_KVTILE_BYTES / 2), &tm_v, kvh * FA_D + h * 64, tok0 + j * FA_BN,
                                 &v_full[vs]);
-                if (++vs == FA_VSTAGES) { vs = 0; vph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // S = Q K^T : A, B K-major
+    } else if (warp == 1 || warp == 2) {
+        // =============================== MMA issuers: warp 1 drives chain 0, warp 2 drives chain 1 ===============================
+        // Two issuing warps so that one chain's softmax hand-off never waits behind the other chain's.
+        // The whole warp runs the control flow (waits, descriptor arithmetic) convergently so the compiler keeps every
+        // tcgen05 operand in uniform registers; only the instructions themselves sit under the elected-lane predicate.
+        {
+            const int n_kv_u = __shfl_sync(0xffffffffu, n_kv, 0);       // warp-uniform trip count
+            const int t = __shfl_sync(0xffffffffu, warp - 1, 0);        // this warp's chain
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, FA_BN, 0, 0);   // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_o = umma_idesc_bf16(128, 128, 0, 1);     // O += P V : A from TMEM, B (V) MN-major
-            const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
-            const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-
-            auto issue_s = [&](int t, int ks) {
-                const uint32_t qa = smem_u32(sQ + t * FA_TILE_BYTES);
-                const uint32_t ka = smem_u32(sK + ks * FA_TILE_BYTES);
+            // Descriptors are base + (byte offset >> 4): the address field is the low 14 bits in 16-byte units and shared
+            // memory tops out below 2^18 bytes, so plain 64-bit adds never carry out of the field.
+            const uint64_t dq0 = umma_desc_k_sw128(smem_u32(sQ));
+            const uint64_t dk0 = umma_desc_k_sw128(smem_u32(sK));
+            const uint64_t dv0 = umma_desc_mn_sw128(smem_u32(sV), FA_KVTILE_BYTES / 2, 1024);
+            auto issue_s = [&](int t, int j) {
+                const uint32_t tS = tmem_base + t * 256 + (j & 1) * 64;
+                const uint64_t dq = dq0 + (uint64_t)(t * (FA_QTILE_BYTES >> 4));
+                const uint64_t dk = dk0 + (uint64_t)((j % FA_KSTAGES) * (FA_KVTILE_BYTES >> 4));
+                uint64_t* bar = &s_full[t * 2 + (j & 1)];
+                if (leader) {
+#ifndef FA_DBG_NOS
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t off = (k >> 2) * (FA_TILE_BYTES / 2) + (k & 3) * 32;      // box, then 32 B per k-step
-                    umma_bf16_ss(tS[t], umma_desc_k_sw128(qa + off), umma_desc_k_sw128(ka + off), idesc_s, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 8; ++k) {      // 16 head-dim elements per step: box k>>2, 32 B inside the swizzle row
+                        const uint64_t qoff = (uint64_t)(((k >> 2) * (FA_QTILE_BYTES / 2) + (k & 3) * 32) >> 4);
+                        const uint64_t koff = (uint64_t)(((k >> 2) * (FA_KVTILE_BYTES / 2) + (k & 3) * 32) >> 4);
+                        umma_bf16_ss(tS, dq + qoff, dk + koff, idesc_s, k > 0 ? 1u : 0u);
+                    }
+#endif
+                    umma_commit(bar);
                 }
-                umma_commit(&s_full[t]);
+                __syncwarp();
             };
-            auto issue_pv = [&](int t, int vs, bool first) {
-                const uint32_t va = smem_u32(sV + vs * FA_TILE_BYTES);
+            auto issue_pv = [&](int t, int j) {
+                const uint32_t tP = tmem_base + t * 256 + (j & 1) * 64;
+                const uint32_t tO = tmem_base + t * 256 + 128;
+                const uint64_t dv = dv0 + (uint64_t)((j % FA_VSTAGES) * (FA_KVTILE_BYTES >> 4));
+                const uint32_t acc0 = (j == 0) ? 0u : 1u;
+                uint64_t* bar = &pv_done[t * 2 + (j & 1)];
+                if (leader) {
+#ifndef FA_DBG_NOPV
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    // 16 keys per step: 16 rows x 128 B = 2048 B into the tile; d halves are 16 KB apart (LBO), 8-row groups 1 KB (SBO)
-                    const uint64_t vd = umma_desc_mn_sw128(va + k * 2048, FA_TILE_BYTES / 2, 1024);
-                    umma_bf16_ts(tO[t], tS[t] + k * 8, vd, idesc_o, (first && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < FA_BN / 16; ++k) {
+                        // 16 keys per step: 16 rows x 128 B = 2048 B into the box; d halves are 8 KB apart (LBO), 8-row groups 1 KB (SBO)
+                        umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)((k * 2048) >> 4), idesc_o, k == 0 ? acc0 : 1u);
+                    }
+#endif
+                    umma_commit(bar);
                 }
+                __syncwarp();
+            };
+            auto commit = [&](uint64_t* bar) {
+                if (leader) umma_commit(bar);
+                __syncwarp();
             };
 
             mbar_wait(q_full, 0);
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0, pph = 0;
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            issue_s(1, 0);
-            umma_commit(&k_empty[0]);                       // K_0 free once both S MMAs retire
-            int ks_next = 1 % FA_KSTAGES;
-            uint32_t kph_next = (FA_KSTAGES == 1) ? 1u : 0u;
-            (void)ks; (void)kph;
-            for (int j = 0; j < n_kv; ++j) {
-                const bool more = (j + 1 < n_kv);
-                mbar_wait(&v_full[vs], vph);
-                if (more) mbar_wait(&k_full[ks_next], kph_next);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    mbar_wait(&p_full[t], pph);
-                    tc_fence_after();
-                    issue_pv(t, vs, j == 0);
-                    if (more) issue_s(t, ks_next);          // overwrites S_t / P_t: ordered after P_t V_j on the tensor pipe
-                    else umma_commit(&o_done[t]);
-                }
-                umma_commit(&v_empty[vs]);
-                if (more) umma_commit(&k_empty[ks_next]);
-                pph ^= 1;
-                if (++vs == FA_VSTAGES) { vs = 0; vph ^= 1; }
-                if (more) { if (++ks_next == FA_KSTAGES) { ks_next = 0; kph_next ^= 1; } }
+            for (int jj = 0; jj < 2 && jj < n_kv_u; ++jj) {
+                mbar_wait(&k_full[jj % FA_KSTAGES], 0);
+                tc_fence_after();
+                issue_s(t, jj);
+                commit(&k_empty[jj % FA_KSTAGES]);
+            }
+            for (int j = 0; j < n_kv_u; ++j) {
+                const bool more = (j + 2 < n_kv_u);
+                mbar_wait(&v_full[j % FA_VSTAGES], (j / FA_VSTAGES) & 1);
+                if (more) mbar_wait(&k_full[(j + 2) % FA_KSTAGES], ((j + 2) / FA_KSTAGES) & 1);
+                mbar_wait(&p_full[t * 2 + (j & 1)], (j >> 1) & 1);
+                tc_fence_after();
+                issue_pv(t, j);
+                if (more) issue_s(t, j + 2);                // overwrites buffer j&1: ordered after P_t(j) V_j (same issuing thread)
+                commit(&v_empty[j % FA_VSTAGES]);
+                if (more) commit(&k_empty[(j + 2) % FA_KSTAGES]);
             }
         }
     } else if (warp >= 4) {
         // =============================== softmax warpgroups ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");       // one query row = 128 fp32 scores in registers
-        const int t = (warp - 4) >> 2;                   // 0: tile A, 1: tile B
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int t = (warp - 4) >> 2;                   // chain
         const int wq = warp & 3;                         // TMEM lane quarter
         const int row = wq * 32 + lane;                  // row within the tile == TMEM lane
         const int qi = q0 + t * FA_BM + row;             // query index within the sequence
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + t * 128;
-        const uint32_t tO = tmem_base + lane_addr + 256 + t * 128;
+        const uint32_t tSbase = tmem_base + lane_addr + t * 256;
+        const uint32_t tO = tSbase + 128;
         float m_run = -INFINITY;                         // running max in raw score units
         float l_run = 0.f;
-        uint32_t sph = 0;
         for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(&s_full[t], sph);
-            sph ^= 1;
+            const uint32_t tS = tSbase + (j & 1) * 64;
+            mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
             tc_fence_after();
-            float s[128];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+#ifdef FA_DBG_NOSOFTMAX
+            tc_fence_before();
+            mbar_arrive(&p_full[t * 2 + (j & 1)]);
+            continue;
+#endif
+            float s[FA_BN];
+            tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
             tmem_ld_wait();
             const int k0 = j * FA_BN;
             const bool need_mask = (k0 + FA_BN > L) || (CAUSAL && (k0 + FA_BN - 1 > q0 + t * FA_BM + wq * 32));
             if (need_mask) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i) {
+                for (int i = 0; i < FA_BN; ++i) {
                     const int kj = k0 + i;
                     if (kj >= L || (CAUSAL && kj > qi)) s[i] = -INFINITY;
                 }
             }
-            float mx = -INFINITY;
+            // row max: four independent chains of 3-input max (FMNMX3)
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, s[i]);
+            for (int i = 0; i < FA_BN; i += 8) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], fmaxf(s[i + 2 * c], s[i + 2 * c + 1]));
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             // lazy rescale: only move the reference max when it would grow by more than 2^8 in the exp2 domain
             const bool need = (mx > m_run) && ((mx - m_run) * p.scale_log2 > 8.0f);
             if (__any_sync(0xffffffffu, need)) {
                 const float m_new = need ? mx : m_run;
                 const float alpha = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_new) * p.scale_log2);
                 if (j > 0) {
-                    // S_t(j) complete implies P_t V_{j-1} retired (in-order tensor pipe): O_t is stable here
+                    // O_t must hold every product issued so far: S_t(j) ready only implies P(j-2) V retired, so wait for
+                    // P(j-1) V explicitly.  Its barrier is in one of two states (that phase pending / complete): skipping
+                    // this wait on other iterations cannot alias the parity.
+                    mbar_wait(&pv_done[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+                    tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t v[32];
@@ -260,26 +321,37 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 m_run = m_new;
             }
             const float mneg = (m_run == -INFINITY) ? 0.f : -m_run * p.scale_log2;
-            float lsum = 0.f;
+            // p = exp2(s * scale - m * scale): packed fp32x2 FMA / add (FFMA2, FADD2); four independent packed row-sum accumulators
+            const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), mn2 = pack_f32x2(mneg, mneg);
+            uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+            uint32_t pk[32];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t pk[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p0 = ex2f(fmaf(s[c * 64 + 2 * i], p.scale_log2, mneg));
-                    const float p1 = ex2f(fmaf(s[c * 64 + 2 * i + 1], p.scale_log2, mneg));
-                    lsum += p0 + p1;
-                    pk[i] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 32; ++i) {
+                const uint64_t x2 = ffma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), sc2, mn2);
+                float p0, p1;
+                if ((FA_EMU_MASK >> i) & 1u) {
+                    ex2_poly_f32x2(x2, p0, p1);
+                } else {
+                    float x0, x1;
+                    unpack_f32x2(x2, x0, x1);
+                    p0 = ex2f(x0); p1 = ex2f(x1);
                 }
-                tmem_st_32x32b_x32(tS + c * 32, pk);
+                acc2[i & 3] = fadd_f32x2(acc2[i & 3], pack_f32x2(p0, p1));
+                pk[i] = pack_bf16x2(p0, p1);
             }
-            l_run += lsum;
+            tmem_st_32x32b_x32(tS, pk);
+            {
+                float a0, a1, b0, b1;
+                unpack_f32x2(fadd_f32x2(acc2[0], acc2[1]), a0, a1);
+                unpack_f32x2(fadd_f32x2(acc2[2], acc2[3]), b0, b1);
+                l_run += (a0 + a1) + (b0 + b1);
+            }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&p_full[t]);
+            mbar_arrive(&p_full[t * 2 + (j & 1)]);
         }
         // ---- epilogue: O_t / l -> bf16 -> global ------------------------------------------
-        mbar_wait(&o_done[t], 0);
+        mbar_wait(&pv_done[t * 2 + ((n_kv - 1) & 1)], ((n_kv - 1) >> 1) & 1);
         tc_fence_after();
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         bf16* dst = p.o + (long long)(tok0 + qi) * p.os + head * FA_D;
@@ -326,8 +398,8 @@ extern "C" int dots_attn_varlen_fwd_tc(const void* q, long long q_stride, const 
     DOTS_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0, "dots_attn_varlen_fwd_tc: 16-byte aligned pointers");
     CUtensorMap tq, tk, tv;
     if (make_tmap_2d_bf16(&tq, q, total_tokens, (uint64_t)n_q_heads * FA_D, q_stride, 128, 64)) return -4;
-    if (make_tmap_2d_bf16(&tk, k, total_tokens, (uint64_t)n_kv_heads * FA_D, k_stride, 128, 64)) return -4;
-    if (make_tmap_2d_bf16(&tv, v, total_tokens, (uint64_t)n_kv_heads * FA_D, v_stride, 128, 64)) return -4;
+    if (make_tmap_2d_bf16(&tk, k, total_tokens, (uint64_t)n_kv_heads * FA_D, k_stride, FA_BN, 64)) return -4;
+    if (make_tmap_2d_bf16(&tv, v, total_tokens, (uint64_t)n_kv_heads * FA_D, v_stride, FA_BN, 64)) return -4;
     FaParams p;
     p.cu = cu_seqlens; p.o = (bf16*)out; p.os = o_stride;
     p.n_q_heads = n_q_heads; p.group = n_q_heads / n_kv_heads;
