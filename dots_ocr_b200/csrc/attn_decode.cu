@@ -31,7 +31,29 @@ struct DecParams {
     long long ctx_max;
     int n_q_heads, n_kv_heads, group, n_splits;
     float scale_log2;
+    // fused QKV finalize (dots_attn_decode_fused): q/k/v of the current token arrive as split-K fp32 partials
+    // [qkv_splits][B][(nq + 2 nkv) * 128] of the QKV GEMM; this kernel adds the bias, applies RoPE, appends k, v to the
+    // cache and keeps q in shared memory.  qkv_partial == nullptr: q is read from p.q (plain dots_attn_decode).
+    const float* qkv_partial;
+    int qkv_splits;
+    const bf16* qkv_bias;
+    const int* pos;
+    const float* inv_freq;
+    bf16* kc_w;
+    bf16* vc_w;
 };
+
+// HF Qwen2 RoPE rounding points (modeling_qwen2.py:102-146): cos/sin are bf16, every product and the sum round to bf16.
+__device__ __forceinline__ void dec_rope_bf16_4(const float (&x1)[4], const float (&x2)[4], int pos, const float* __restrict__ inv_freq,
+                                                int i0, float (&o1)[4], float (&o2)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float ang = __fmul_rn((float)pos, inv_freq[i0 + j]);
+        const float c = bf16_round(cosf(ang)), sn = bf16_round(sinf(ang));
+        o1[j] = bf16_round(__fadd_rn(bf16_round(__fmul_rn(x1[j], c)), bf16_round(__fmul_rn(-x2[j], sn))));
+        o2[j] = bf16_round(__fadd_rn(bf16_round(__fmul_rn(x2[j], c)), bf16_round(__fmul_rn(x1[j], sn))));
+    }
+}
 
 __device__ __forceinline__ void dec_load_tile(uint8_t* dst, const bf16* gsrc_rows, int key0, int key_end, int lane) {
     // 16 rows x 16 chunks; 32 lanes -> 8 chunks each
@@ -67,13 +89,75 @@ attn_decode_kernel(const DecParams p) {
     const bf16* vbase = p.vc + ((long long)b * p.n_kv_heads + kvh) * p.ctx_max * DEC_D;
 
     // Q tile: rows 0..G-1 = the group's q heads, rows G..15 zero
-    {
+    if (p.qkv_partial == nullptr) {
         const bf16* qg = p.q + (long long)b * p.n_q_heads * DEC_D + (long long)kvh * p.group * DEC_D;
         for (int idx = tid; idx < 16 * 16; idx += DEC_THREADS) {
             const int r = idx >> 4, c = idx & 15;
             uint4 val = make_uint4(0, 0, 0, 0);
             if (r < p.group) val = *reinterpret_cast<const uint4*>(qg + r * DEC_D + c * 8);
             *reinterpret_cast<uint4*>(sQ + swz128(r, c)) = val;
+        }
+    } else {
+        // ---- fused QKV finalize: split-K reduce (fixed order) + bias + RoPE; q -> sQ, k/v -> cache row `pos` ----
+        for (int idx = tid; idx < (16 - p.group) * 16; idx += DEC_THREADS) {
+            const int r = p.group + (idx >> 4), c = idx & 15;
+            *reinterpret_cast<uint4*>(sQ + swz128(r, c)) = make_uint4(0, 0, 0, 0);
+        }
+        const int posb = p.pos[b];
+        const bool owns_new = (posb >= k_begin) && (posb < k_end);        // the split whose key range holds the new token
+        const int N = (p.n_q_heads + 2 * p.n_kv_heads) * DEC_D;
+        const long long sstride = (long long)(gridDim.z) * N;
+        const int n_units = (p.group + 2) * 16;                            // (head, 4-column pair chunk)
+        for (int u = tid; u < n_units; u += DEC_THREADS) {
+            const int hl = u >> 4, c4 = u & 15;
+            if (hl >= p.group && !owns_new) continue;
+            const int col0 = (hl < p.group ? (kvh * p.group + hl)
+                                           : (hl == p.group ? p.n_q_heads + kvh : p.n_q_heads + p.n_kv_heads + kvh)) * DEC_D + c4 * 4;
+            const float* src = p.qkv_partial + (long long)b * N + col0;
+            float x1[4] = {0.f, 0.f, 0.f, 0.f}, x2[4] = {0.f, 0.f, 0.f, 0.f};
+            int sidx = 0;
+            for (; sidx + 4 <= p.qkv_splits; sidx += 4) {
+                float4 a[4], d[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    a[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride);
+                    d[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride + 64);
+                }
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    x1[0] += a[w].x; x1[1] += a[w].y; x1[2] += a[w].z; x1[3] += a[w].w;
+                    x2[0] += d[w].x; x2[1] += d[w].y; x2[2] += d[w].z; x2[3] += d[w].w;
+                }
+            }
+            for (; sidx < p.qkv_splits; ++sidx) {
+                const float4 a = *reinterpret_cast<const float4*>(src + sidx * sstride);
+                const float4 d = *reinterpret_cast<const float4*>(src + sidx * sstride + 64);
+                x1[0] += a.x; x1[1] += a.y; x1[2] += a.z; x1[3] += a.w;
+                x2[0] += d.x; x2[1] += d.y; x2[2] += d.z; x2[3] += d.w;
+            }
+            const uint2 b1 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0);
+            const uint2 b2 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0 + 64);
+            x1[0] = bf16_round(x1[0] + bf16_lo(b1.x)); x1[1] = bf16_round(x1[1] + bf16_hi(b1.x));
+            x1[2] = bf16_round(x1[2] + bf16_lo(b1.y)); x1[3] = bf16_round(x1[3] + bf16_hi(b1.y));
+            x2[0] = bf16_round(x2[0] + bf16_lo(b2.x)); x2[1] = bf16_round(x2[1] + bf16_hi(b2.x));
+            x2[2] = bf16_round(x2[2] + bf16_lo(b2.y)); x2[3] = bf16_round(x2[3] + bf16_hi(b2.y));
+            float o1[4], o2[4];
+            if (hl <= p.group) {
+                dec_rope_bf16_4(x1, x2, posb, p.inv_freq, c4 * 4, o1, o2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { o1[j] = x1[j]; o2[j] = x2[j]; }
+            }
+            const uint2 r1 = make_uint2(pack_bf16x2(o1[0], o1[1]), pack_bf16x2(o1[2], o1[3]));
+            const uint2 r2 = make_uint2(pack_bf16x2(o2[0], o2[1]), pack_bf16x2(o2[2], o2[3]));
+            if (hl < p.group) {
+                *reinterpret_cast<uint2*>(sQ + swz128(hl, c4 >> 1) + (c4 & 1) * 8) = r1;
+                *reinterpret_cast<uint2*>(sQ + swz128(hl, 8 + (c4 >> 1)) + (c4 & 1) * 8) = r2;
+            } else {
+                bf16* dst = (hl == p.group ? p.kc_w : p.vc_w) + (((long long)b * p.n_kv_heads + kvh) * p.ctx_max + posb) * DEC_D + c4 * 4;
+                *reinterpret_cast<uint2*>(dst) = r1;
+                *reinterpret_cast<uint2*>(dst + 64) = r2;
+            }
         }
     }
     __syncthreads();
@@ -236,16 +320,12 @@ attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __rest
 
 using namespace dots;
 
-extern "C" int dots_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* ctx_len, void* out,
-                                float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
-                                long long ctx_max, int n_splits, float softmax_scale, void* stream) {
-    DOTS_REQUIRE(head_dim == DEC_D, "dots_attn_decode: head_dim must be 128");
+static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_heads, int head_dim, int n_splits, float softmax_scale,
+                              void* stream, const char* who) {
+    DOTS_REQUIRE(head_dim == DEC_D, "%s: head_dim must be 128", who);
     DOTS_REQUIRE(batch > 0 && n_q_heads % n_kv_heads == 0 && n_q_heads / n_kv_heads <= 8,
-                 "dots_attn_decode: bad heads %d/%d (group must be <= 8)", n_q_heads, n_kv_heads);
-    DOTS_REQUIRE(n_splits >= 1 && (n_splits == 1 || (part_o && part_ml)), "dots_attn_decode: n_splits>1 needs partial buffers");
-    DecParams p;
-    p.q = (const bf16*)q; p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.ctx_len = ctx_len;
-    p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
+                 "%s: bad heads %d/%d (group must be <= 8)", who, n_q_heads, n_kv_heads);
+    DOTS_REQUIRE(n_splits >= 1 && (n_splits == 1 || (p.part_o && p.part_ml)), "%s: n_splits>1 needs partial buffers", who);
     p.n_q_heads = n_q_heads; p.n_kv_heads = n_kv_heads; p.group = n_q_heads / n_kv_heads; p.n_splits = n_splits;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -257,7 +337,29 @@ extern "C" int dots_attn_decode(const void* q, const void* k_cache, const void* 
     dim3 grid(n_splits, n_kv_heads, batch);
     DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, p));
     if (n_splits > 1) {
-        DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, part_o, part_ml, (bf16*)out, n_splits));
+        DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, p.part_o, p.part_ml, p.out, n_splits));
     }
     return 0;
+}
+
+extern "C" int dots_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* ctx_len, void* out,
+                                float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
+                                long long ctx_max, int n_splits, float softmax_scale, void* stream) {
+    DecParams p{};
+    p.q = (const bf16*)q; p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.ctx_len = ctx_len;
+    p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
+    return launch_attn_decode(p, batch, n_q_heads, n_kv_heads, head_dim, n_splits, softmax_scale, stream, "dots_attn_decode");
+}
+
+extern "C" int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, const void* qkv_bias, const int* pos, const float* inv_freq,
+                                      void* k_cache, void* v_cache, const int* ctx_len, void* out, float* part_o, float* part_ml,
+                                      int batch, int n_q_heads, int n_kv_heads, int head_dim, long long ctx_max, int n_splits,
+                                      float softmax_scale, void* stream) {
+    DOTS_REQUIRE(qkv_partial && qkv_splits >= 1 && qkv_bias && pos && inv_freq, "dots_attn_decode_fused: missing QKV inputs");
+    DecParams p{};
+    p.q = nullptr; p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.ctx_len = ctx_len;
+    p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
+    p.qkv_partial = qkv_partial; p.qkv_splits = qkv_splits; p.qkv_bias = (const bf16*)qkv_bias; p.pos = pos; p.inv_freq = inv_freq;
+    p.kc_w = (bf16*)k_cache; p.vc_w = (bf16*)v_cache;
+    return launch_attn_decode(p, batch, n_q_heads, n_kv_heads, head_dim, n_splits, softmax_scale, stream, "dots_attn_decode_fused");
 }

@@ -541,8 +541,8 @@ __global__ void decode_qkv_rope_append_kernel(const float* __restrict__ partial,
     }
 }
 
-// act = bf16( bf16(silu(bf16 gate)) * bf16 up ), gate/up interleaved per 256-column block
-// ([128 gate | 128 up], the layout the prefill SWIGLU epilogue uses), partial [splits][B][2I].
+// act = bf16( bf16(silu(bf16 gate)) * bf16 up ), gate/up interleaved per 128-column block
+// ([64 gate | 64 up], the layout the SWIGLU epilogues use), partial [splits][B][2I].
 __global__ void decode_swiglu_kernel(const float* __restrict__ partial, int splits, bf16* __restrict__ act, int B, int I) {
     pdl_wait();
     pdl_launch_dependents();
@@ -551,12 +551,12 @@ __global__ void decode_swiglu_kernel(const float* __restrict__ partial, int spli
     if (idx >= B * chunks) return;
     const int b = idx / chunks, c = idx % chunks;
     const int col = c * 8;
-    const int gcol = (col >> 7) * 256 + (col & 127);
+    const int gcol = (col >> 6) * 128 + (col & 63);
     float gsum[8], usum[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { gsum[j] = 0.f; usum[j] = 0.f; }
     sum_splits8(partial + (long long)b * (2LL * I) + gcol, (long long)B * 2LL * I, splits, gsum);
-    sum_splits8(partial + (long long)b * (2LL * I) + gcol + 128, (long long)B * 2LL * I, splits, usum);
+    sum_splits8(partial + (long long)b * (2LL * I) + gcol + 64, (long long)B * 2LL * I, splits, usum);
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -675,7 +675,7 @@ extern "C" int dots_decode_qkv_rope_append(const float* partial, int splits, con
 }
 
 extern "C" int dots_decode_swiglu(const float* partial, int splits, void* act, int batch, int inter, void* stream) {
-    DOTS_REQUIRE(batch > 0 && splits > 0 && inter % 128 == 0, "dots_decode_swiglu: intermediate size must be a multiple of 128");
+    DOTS_REQUIRE(batch > 0 && splits > 0 && inter % 64 == 0, "dots_decode_swiglu: intermediate size must be a multiple of 64");
     const int n = batch * (inter / 8);
     DOTS_CHECK_CUDA(launch_ex(decode_swiglu_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), ST(stream), true, partial, splits, (bf16*)act, batch, inter));
     return 0;

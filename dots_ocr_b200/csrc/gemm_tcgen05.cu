@@ -32,7 +32,7 @@ struct GemmParams {
     long long ldr;
 };
 
-constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T; }
+constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
 
 template <int BLOCK_N, int EPI>
 struct GemmSmem {
@@ -45,7 +45,9 @@ struct GemmSmem {
     static constexpr int STAGES = SWAP ? (BLOCK_N >= 256 ? 2 : 4) : (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
     static constexpr int MIN_CTAS = (SWAP && BLOCK_N <= 128) ? 2 : 1;
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+    // SWIGLU_T: the up-projection warps hand their bf16-rounded values to the gate warps through shared memory
+    static constexpr int XCH_BYTES = (EPI == DOTS_EPI_SWIGLU_T) ? BLOCK_N * 64 * 2 : 0;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + XCH_BYTES + 1024;   // + alignment slack
     static constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N <= 32) ? 32 : (ACC_STAGES * BLOCK_N <= 64) ? 64
                                    : (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256) ? 256 : 512;
 };
@@ -76,6 +78,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tmem_full = bars + 2 * STAGES;         // [ACC_STAGES]
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+    bf16* xch = reinterpret_cast<bf16*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);   // [BLOCK_N][64] (SWIGLU_T only)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -103,7 +106,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);      // warp-uniform for the compiler
     pdl_launch_dependents();        // the next kernel of the stream may begin its own prologue / weight prefetch
 
     if (warp == 0) {
@@ -149,8 +152,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop convergently (uniform registers for descriptors / TMEM addresses); only the
+        // tcgen05 instructions sit under the elected-lane predicate.
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+            const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem_a));
+            const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b));
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -166,17 +174,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * S::A_BYTES));
-                    const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * S::B_BYTES));
+                    const uint64_t da = da0 + (uint64_t)(stage * (S::A_BYTES >> 4));
+                    const uint64_t db = db0 + (uint64_t)(stage * (S::B_BYTES >> 4));
+                    const uint32_t first = (kb > kb0) ? 1u : 0u;
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the >>4 address field
-                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the >>4 address field
+                            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : first);
+                        }
+                        umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                        if (kb + 1 == kb1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
                     }
-                    umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -195,14 +207,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
 
             if constexpr (EPI == DOTS_EPI_SWIGLU) {
-                // B rows are interleaved per 256-block: [128 gate rows | 128 up rows]; out has N/2 columns.
+                // B rows are interleaved per 128-block: [64 gate rows | 64 up rows]; out has N/2 columns.
                 static_assert(EPI != DOTS_EPI_SWIGLU || BLOCK_N == 256, "swiglu epilogue needs BLOCK_N=256");
                 bf16* out = reinterpret_cast<bf16*>(p.out);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t g[32], u[32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, g);
-                    tmem_ld_32x32b_x32(t_row + 128 + c * 32, u);
+                    tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + (c & 1) * 32, g);
+                    tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + 64 + (c & 1) * 32, u);
                     tmem_ld_wait();
                     const int col = n_blk * 128 + c * 32;
                     if (row < p.M) {
@@ -221,6 +233,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                 *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                     }
                 }
+            } else if constexpr (EPI == DOTS_EPI_SWIGLU_T) {
+                // swap-AB decode GEMM over the gate|up weight: tile rows 0-63 are gate features, rows 64-127 the matching up
+                // features (warps 0,1 / 2,3 of this group).  Up warps publish bf16(up) through shared memory, gate warps
+                // finish  act[b][f] = bf16( bf16(silu(bf16 g)) * bf16 u )  -- the same rounding points as the prefill epilogue.
+                bf16* out = reinterpret_cast<bf16*>(p.out);
+                const int fl = (wq & 1) * 32 + lane;                 // feature within the 64-block
+                if (wq >= 2) {
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(t_row + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) xch[(c * 32 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+                if (wq < 2) {
+                    const int f = m_blk * 64 + fl;
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(t_row + c * 32, v);
+                        tmem_ld_wait();
+                        if (f < p.M / 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int b = n_blk * BLOCK_N + c * 32 + j;
+                                if (b < p.N) {
+                                    const float gv = bf16_round(__uint_as_float(v[j]));
+                                    const float uv = __bfloat162float(xch[(c * 32 + j) * 64 + fl]);
+                                    out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
+                                }
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // xch is free for the next tile
             } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
                 // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
                 // partial[split][b][feature] fp32; lanes write consecutive features (coalesced).
@@ -476,5 +526,34 @@ extern "C" int dots_gemm_skinny_bf16(const void* X, long long ldx, const void* W
         case 64: return launch_gemm<64, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
         case 128: return launch_gemm<128, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
         default: return launch_gemm<256, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
+    }
+}
+
+// Decode gate|up GEMM with the SwiGLU fused into the epilogue (no split-K: 2I/128 tiles already cover the SMs).
+// W is the interleaved gate|up weight [2I, K] ([64 gate | 64 up] per 128 rows); act [batch, I] bf16.
+extern "C" int dots_gemm_skinny_swiglu_bf16(const void* X, long long ldx, const void* W, long long ldw, void* act, long long ld_act,
+                                            int batch, int two_i, int K, void* stream) {
+    DOTS_REQUIRE(batch > 0 && batch <= 256 && two_i > 0 && two_i % 128 == 0 && K > 0, "dots_gemm_skinny_swiglu_bf16: bad shape batch=%d 2I=%d K=%d",
+                 batch, two_i, K);
+    DOTS_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "dots_gemm_skinny_swiglu_bf16: K and pitches must be multiples of 8");
+    GemmParams p{};
+    p.static_is_b = 0;
+    p.M = two_i; p.N = batch; p.K = K;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb_per_split = p.num_k_blocks;
+    p.splits = 1;
+    p.out = act; p.ldo = ld_act;
+    p.m_blocks = two_i / BLOCK_M;
+    p.n_blocks = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta, tb;
+    if (make_tmap_2d_bf16(&ta, W, two_i, K, ldw, BLOCK_M)) return -4;
+    const int bn = batch <= 32 ? 32 : batch <= 64 ? 64 : batch <= 128 ? 128 : 256;
+    if (make_tmap_2d_bf16(&tb, X, batch, K, ldx, bn)) return -4;
+    switch (bn) {
+        case 32: return launch_gemm<32, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
+        case 64: return launch_gemm<64, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
+        case 128: return launch_gemm<128, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
+        default: return launch_gemm<256, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
     }
 }

@@ -8,7 +8,8 @@ handful of index-array constructions on the host side.
 
 Layout in HBM (all bf16 unless noted):
   * weights: nn.Linear layout [out, in]; fused qkv; gate|up (fc1|fc3) interleaved per 256 rows
-    as [128 gate | 128 up] so the SwiGLU epilogue finds both halves in one accumulator tile.
+    as [64 gate | 64 up] per 128 rows so both SwiGLU epilogues (prefill: 256-wide accumulator tile; decode swap-AB:
+    128-row tile) find matching gate/up features in one tile.
   * activations: token-major packed [sum_tokens, width] (no padding between sequences).
   * KV cache: [layers, batch, kv_heads, ctx_max, 128], appended in place.
 """
@@ -27,8 +28,8 @@ from .config import DotsConfig
 def _interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     I, H = gate.shape
     assert I % 128 == 0, "intermediate size must be a multiple of 128"
-    g = gate.view(I // 128, 128, H)
-    u = up.view(I // 128, 128, H)
+    g = gate.view(I // 64, 64, H)
+    u = up.view(I // 64, 64, H)
     return torch.stack([g, u], dim=1).reshape(2 * I, H).contiguous()
 
 
@@ -207,7 +208,8 @@ class Engine:
             o=ops.pick_splits(tiles(H), kb(t.num_attention_heads * t.head_dim), self.sms),
             gu=ops.pick_splits(tiles(2 * I), kb(H), self.sms),
             down=ops.pick_splits(tiles(H), kb(I), self.sms),
-            attn=max(1, min(16, (3 * self.sms) // max(1, B * t.num_key_value_heads))),
+            # one CTA per (sequence, kv head) once that alone covers most SMs (no combine kernel); flash-decoding splits below
+            attn=1 if B * t.num_key_value_heads >= (3 * self.sms) // 4 else max(1, min(16, (2 * self.sms) // max(1, B * t.num_key_value_heads))),
         )
 
     def _decode_step(self, st: dict):
@@ -220,14 +222,11 @@ class Engine:
         n_layers = len(self.t_layers)
         for li, L in enumerate(self.t_layers):
             ops.gemm_skinny(st["normed"], L["qkv_w"], pl["qkv"], partial=st["partial"])
-            ops.decode_qkv_rope_append(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["q"], st["kc"][li],
-                                       st["vc"][li], st["ctx_max"], nq, nkv)
-            ops.attn_decode(st["q"], st["kc"][li], st["vc"][li], st["ctx_len"], st["attn"], nq, nkv, st["ctx_max"], pl["attn"],
-                            scale, st["part_o"], st["part_ml"])
+            ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
+                                  st["ctx_len"], st["attn"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"])
             ops.gemm_skinny(st["attn"], L["o"], pl["o"], partial=st["partial"])
             ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed"], t.rms_norm_eps)
-            ops.gemm_skinny(st["normed"], L["gu"], pl["gu"], partial=st["partial"])
-            ops.decode_swiglu(st["partial"], pl["gu"], st["act"])
+            ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
             ops.gemm_skinny(st["act"], L["down"], pl["down"], partial=st["partial"])
             nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
             ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed"], t.rms_norm_eps)
@@ -255,7 +254,7 @@ class Engine:
 
     def launches_per_decode_step(self, B: int) -> int:
         pl = self._decode_plan(B)
-        per_layer = 9 + (1 if pl["attn"] > 1 else 0)
+        per_layer = 7 + (1 if pl["attn"] > 1 else 0)
         return 1 + per_layer * len(self.t_layers) + 2
 
     @torch.no_grad()

@@ -93,6 +93,20 @@ def gemm_skinny(x: torch.Tensor, w: torch.Tensor, splits: int = 1, partial: Opti
     return out_bf16 if out_bf16 is not None else partial
 
 
+def gemm_skinny_swiglu(x: torch.Tensor, w_gu: torch.Tensor, act: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode gate|up projection with the SwiGLU fused into the GEMM epilogue: act [B, I] from x [B, K], w_gu [2I, K]."""
+    _bf16_2d(x, "x"); _bf16_2d(w_gu, "w_gu")
+    B, Kd = x.shape
+    two_i = w_gu.shape[0]
+    if act is None:
+        act = torch.empty((B, two_i // 2), device=x.device, dtype=torch.bfloat16)
+    _bf16_2d(act, "act")
+    rc = _lib.load().dots_gemm_skinny_swiglu_bf16(_p(x), _ll(x.stride(0)), _p(w_gu), _ll(w_gu.stride(0)), _p(act), _ll(act.stride(0)),
+                                                  B, two_i, Kd, _stream())
+    _lib.check(rc, "dots_gemm_skinny_swiglu_bf16")
+    return act
+
+
 def pick_splits(n_tiles: int, num_kb: int, sms: int = 148) -> int:
     """Largest valid split-K factor s with n_tiles * s <= sms (every split non-empty)."""
     best = 1
@@ -149,6 +163,23 @@ def attn_decode(q, k_cache, v_cache, ctx_len, out, n_q_heads: int, n_kv_heads: i
                                       B, n_q_heads, n_kv_heads, head_dim, _ll(ctx_max), n_splits, C.c_float(scale),
                                       _stream())
     _lib.check(rc, "dots_attn_decode")
+    return out
+
+
+def attn_decode_fused(partial, qkv_splits: int, bias, pos, inv_freq, k_cache, v_cache, ctx_len, out, n_q_heads: int,
+                      n_kv_heads: int, ctx_max: int, n_splits: int, scale: float, part_o=None, part_ml=None, head_dim: int = 128):
+    """QKV finalize (split-K reduce + bias + RoPE + KV append) fused into the decode attention kernel."""
+    B = out.shape[0]
+    assert ctx_len.dtype == torch.int32 and pos.dtype == torch.int32 and partial.dtype == torch.float32
+    if n_splits > 1:
+        if part_o is None:
+            part_o = torch.empty((B, n_q_heads, n_splits, head_dim), device=out.device, dtype=torch.float32)
+        if part_ml is None:
+            part_ml = torch.empty((B, n_q_heads, n_splits, 2), device=out.device, dtype=torch.float32)
+    rc = _lib.load().dots_attn_decode_fused(_p(partial), qkv_splits, _p(bias), _p(pos), _p(inv_freq), _p(k_cache), _p(v_cache),
+                                            _p(ctx_len), _p(out), _p(part_o), _p(part_ml), B, n_q_heads, n_kv_heads, head_dim,
+                                            _ll(ctx_max), n_splits, C.c_float(scale), _stream())
+    _lib.check(rc, "dots_attn_decode_fused")
     return out
 
 

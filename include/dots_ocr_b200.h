@@ -34,10 +34,11 @@ extern "C" {
 #define DOTS_EPI_BIAS 1          /* out = bf16(acc + bias[n]) */
 #define DOTS_EPI_BIAS_GELU 2     /* out = bf16(gelu_erf(bf16(acc + bias[n])))          [V]:196-212 */
 #define DOTS_EPI_RESIDUAL 3      /* out = bf16(bf16(acc) + residual[m, n])             [V]:466,472  [Q]:302,308 */
-#define DOTS_EPI_SWIGLU 4        /* W rows interleaved per 256: [128 gate | 128 up];
+#define DOTS_EPI_SWIGLU 4        /* W rows interleaved per 128: [64 gate | 64 up];
                                     out[m, N/2] = bf16(bf16(silu(bf16 g)) * bf16 u)     [V]:334-356  [Q]:46-48 */
 #define DOTS_EPI_F32_PARTIAL_T 5 /* internal: swap-AB split-K partials */
 #define DOTS_EPI_BF16_T 6        /* internal: swap-AB transposed bf16 store */
+#define DOTS_EPI_SWIGLU_T 7      /* internal: swap-AB gate|up GEMM with fused SwiGLU */
 
 DOTS_API const char* dots_last_error(void);
 DOTS_API int dots_abi_version(void);
@@ -65,6 +66,11 @@ DOTS_API int dots_gemm_skinny_bf16(const void* X, long long ldx, const void* W, 
                           void* out_bf16, long long ldo, const void* bias, int batch, int N, int K, int splits,
                           void* stream);
 
+/* Decode gate|up projection with SwiGLU fused: act[b, I] = bf16(bf16(silu(bf16 g)) * bf16 u), W = interleaved gate|up weight
+ * [2I, K] as for DOTS_EPI_SWIGLU.  Replaces dots_gemm_skinny_bf16 + dots_decode_swiglu for one decode step ([Q]:46-48). */
+DOTS_API int dots_gemm_skinny_swiglu_bf16(const void* X, long long ldx, const void* W, long long ldw, void* act, long long ld_act,
+                                 int batch, int two_i, int K, void* stream);
+
 /* ---- attention ------------------------------------------------------------------------------ */
 
 /* Variable-length fused attention, head_dim 128.  q/k/v are token-major with per-token strides
@@ -91,6 +97,15 @@ DOTS_API int dots_attn_varlen_fwd_tc(const void* q, long long q_stride, const vo
 DOTS_API int dots_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* ctx_len, void* out,
                      float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
                      long long ctx_max, int n_splits, float softmax_scale, void* stream);
+
+/* dots_attn_decode with the QKV finalize fused in front: the current token's q/k/v arrive as the split-K fp32 partials
+ * qkv_partial [qkv_splits][batch][(n_q_heads + 2 n_kv_heads) * 128] of dots_gemm_skinny_bf16; the kernel reduces them in split
+ * order, adds qkv_bias, applies HF's bf16 RoPE at pos[b] ([Q]:102-146), appends k, v at cache[b, :, pos[b]]
+ * (cache_utils.py:119-120) and attends with q held in shared memory.  Requires ctx_len[b] == pos[b] + 1. */
+DOTS_API int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, const void* qkv_bias, const int* pos,
+                           const float* inv_freq, void* k_cache, void* v_cache, const int* ctx_len, void* out,
+                           float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
+                           long long ctx_max, int n_splits, float softmax_scale, void* stream);
 
 /* ---- HBM-bound elementwise / reduction kernels ------------------------------------------------ */
 

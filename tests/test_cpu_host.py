@@ -173,8 +173,10 @@ def test_gate_up_interleave_layout():
     u = -g
     w = _interleave_gate_up(g, u)
     assert w.shape == (512, 2)
-    assert torch.equal(w[:128], g[:128]) and torch.equal(w[128:256], u[:128])
-    assert torch.equal(w[256:384], g[128:]) and torch.equal(w[384:], u[128:])
+    # [64 gate | 64 up] per 128 rows (layout shared by the prefill SWIGLU epilogue and the decode swap-AB epilogue)
+    for blk in range(4):
+        assert torch.equal(w[blk * 128: blk * 128 + 64], g[blk * 64: blk * 64 + 64])
+        assert torch.equal(w[blk * 128 + 64: blk * 128 + 128], u[blk * 64: blk * 64 + 64])
 
 
 def test_engine_refuses_cpu_and_missing_library(monkeypatch):

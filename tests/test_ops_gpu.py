@@ -92,6 +92,52 @@ def test_gemm_swiglu(M, I, K, gen):
     assert _rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,I,K", [(1, 256, 512), (7, 1024, 1536), (64, 8960, 1536), (33, 4224, 1536), (130, 512, 768)])
+def test_gemm_skinny_swiglu(B, I, K, gen):
+    """Fused decode gate|up + SwiGLU == unfused skinny GEMM partials + decode_swiglu (same rounding points), and ~ fp32 reference."""
+    from dots_ocr_b200.engine import _interleave_gate_up
+    ops = _ops()
+    x, wg, wu = _rand((B, K), gen), _rand((I, K), gen, 0.03), _rand((I, K), gen, 0.03)
+    w = _interleave_gate_up(wg, wu)
+    act = torch.full((B, I), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_skinny_swiglu(x, w, act)
+    part = ops.gemm_skinny(x, w, 1)
+    act2 = torch.empty_like(act)
+    ops.decode_swiglu(part, 1, act2)
+    assert torch.equal(act, act2)
+    g, u = _bf(x.float() @ wg.float().t()), _bf(x.float() @ wu.float().t())
+    assert _rel_err(act, torch.nn.functional.silu(g) * u) < 1e-2
+
+
+def test_attn_decode_fused_matches_unfused(gen):
+    """QKV finalize fused into the decode attention kernel == decode_qkv_rope_append + attn_decode, bit for bit."""
+    ops = _ops()
+    nq, nkv = 12, 2
+    N = (nq + 2 * nkv) * 128
+    for (B, splits_qkv, n_splits, ctxs) in [(3, 8, 1, [5, 130, 64]), (2, 3, 4, [700, 2137]), (64, 8, 1, None), (1, 1, 16, [1])]:
+        if ctxs is None:
+            ctxs = [int(v) for v in torch.randint(1, 1900, (B,), generator=torch.Generator().manual_seed(5))]
+        ctx_max = max(ctxs) + 9
+        part = torch.randn((splits_qkv, B, N), generator=gen, device=DEV)
+        bias = _rand((N,), gen, 0.1)
+        ctx = torch.tensor(ctxs, dtype=torch.int32, device=DEV)
+        pos = ctx - 1
+        inv_freq = (1.0 / (1e6 ** (torch.arange(0, 128, 2, dtype=torch.int64).float() / 128))).to(DEV)
+        kc0, vc0 = _rand((B, nkv, ctx_max, 128), gen), _rand((B, nkv, ctx_max, 128), gen)
+        # unfused
+        kc, vc = kc0.clone(), vc0.clone()
+        q = torch.empty((B, nq * 128), device=DEV, dtype=torch.bfloat16)
+        ops.decode_qkv_rope_append(part, splits_qkv, bias, pos, inv_freq, q, kc, vc, ctx_max, nq, nkv)
+        ref = torch.empty_like(q)
+        ops.attn_decode(q, kc, vc, ctx, ref, nq, nkv, ctx_max, n_splits, 128 ** -0.5)
+        # fused
+        kc2, vc2 = kc0.clone(), vc0.clone()
+        out = torch.full_like(q, float("nan"))
+        ops.attn_decode_fused(part, splits_qkv, bias, pos, inv_freq, kc2, vc2, ctx, out, nq, nkv, ctx_max, n_splits, 128 ** -0.5)
+        assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+        assert torch.equal(out, ref), (B, float((out.float() - ref.float()).abs().max()))
+
+
 @pytest.mark.parametrize("B,N,K,splits", [(1, 1024, 768, 12), (7, 2048, 1536, 8), (64, 1536, 8960, 12), (64, 17920, 1536, 1),
                                           (33, 1536, 1536, 12), (130, 2048, 1536, 4)])
 def test_gemm_skinny_partials(B, N, K, splits, gen):
@@ -329,7 +375,7 @@ def test_decode_finalize_kernels(gen):
     part = torch.randn((2, B, 2 * I), generator=gen, device=DEV)
     act = torch.empty((B, I), device=DEV, dtype=torch.bfloat16)
     ops.decode_swiglu(part, 2, act)
-    tot = (part[0] + part[1]).view(B, I // 128, 2, 128)
+    tot = (part[0] + part[1]).view(B, I // 64, 2, 64)
     g, u = _bf(tot[:, :, 0].reshape(B, I)), _bf(tot[:, :, 1].reshape(B, I))
     ref = torch.nn.functional.silu(g) * u
     assert _frac_exact(act, ref) > 0.999 and _rel_err(act, ref) < 8e-3
