@@ -1,11 +1,18 @@
-// Decode-step attention over the in-place KV cache (SURVEY.md §8a rows a18/a19, decode half).
+// Decode-step attention over the in-place KV cache (SURVEY.md §8a rows a17-a19, decode half).
 //
-// One query token per sequence, grouped-query: the G q-heads that share a kv-head are packed into
-// the 16-row M dimension of mma.sync so K and V are read from HBM exactly once per step.
-// Keys are split (a) across CTAs (grid.x = n_splits, "flash decoding") and (b) across the 4 warps
-// of a CTA, each warp streaming its own 16-key tiles through a private cp.async double buffer.
-// Partial (m, l, O) triples are merged in shared memory, then across splits by a small combine
-// kernel.  This kernel is HBM-bound: bytes = 2 * ctx * 256 B per (sequence, kv head).
+// One query token per sequence, grouped-query: the G q-heads that share a kv-head are packed into the 16-row M dimension
+// of mma.sync so K and V are read from HBM exactly once per step.  The kernel is HBM-bound (2 * ctx * 256 B per
+// (sequence, kv head)); what matters is bytes in flight, so K/V arrive through a TMA-fed ring:
+//
+//   warp 4 (one lane)  producer: 64-key K and V tiles (16 KB each, 128-B swizzle boxes) into a 3-stage mbarrier ring.
+//                      Tiles that cannot contain the token being appended are requested BEFORE the programmatic-dependent-
+//                      launch wait, i.e. while the QKV GEMM of this layer is still running.
+//   warps 0-3          consumers: warp w owns keys [16w, 16w+16) of every tile (QK^T, online softmax, PV with mma.sync),
+//                      fixed-order merge of the four partial (m, l, O) through shared memory at the end.
+//
+// Keys are additionally split across CTAs (grid.x = n_splits, "flash decoding") and merged by a small combine kernel.
+// With qkv_partial != nullptr the QKV finalize of the current token (split-K reduce + bias + RoPE + KV append) runs in
+// the prologue of this kernel.
 #include "common.h"
 #include "ptx.cuh"
 #include "mma_sm80.cuh"
@@ -14,11 +21,14 @@
 namespace dots {
 
 constexpr int DEC_D = 128;
-constexpr int DEC_TILE = 16;                 // keys per warp tile
-constexpr int DEC_WARPS = 4;
-constexpr int DEC_THREADS = DEC_WARPS * 32;
-constexpr int DEC_TILE_BYTES = DEC_TILE * DEC_D * 2;                       // 4 KB
-constexpr int DEC_SMEM = 4096 /*Q*/ + DEC_WARPS * 4 * DEC_TILE_BYTES;     // Q + per-warp 2x(K,V) = 68 KB
+constexpr int DEC_TILE = 16;                 // keys per warp per ring tile
+constexpr int DEC_WARPS = 4;                 // consumer warps
+constexpr int DEC_THREADS = (DEC_WARPS + 1) * 32;                          // + producer warp
+constexpr int DEC_RING_KEYS = DEC_TILE * DEC_WARPS;                        // 64 keys per ring tile
+constexpr int DEC_BOX_BYTES = DEC_RING_KEYS * 128;                         // [64 keys][64 dims] bf16 = 8 KB (one swizzle box)
+constexpr int DEC_STAGE_BYTES = 4 * DEC_BOX_BYTES;                         // K lo | K hi | V lo | V hi = 32 KB
+constexpr int DEC_STAGES = 3;
+constexpr int DEC_SMEM = 1024 /*align*/ + 4096 /*Q*/ + DEC_STAGES * DEC_STAGE_BYTES + 256 /*barriers*/;
 
 struct DecParams {
     const bf16* q;            // [B, n_q_heads * 128]
@@ -55,43 +65,86 @@ __device__ __forceinline__ void dec_rope_bf16_4(const float (&x1)[4], const floa
     }
 }
 
-__device__ __forceinline__ void dec_load_tile(uint8_t* dst, const bf16* gsrc_rows, int key0, int key_end, int lane) {
-    // 16 rows x 16 chunks; 32 lanes -> 8 chunks each
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int idx = lane + j * 32;
-        const int r = idx >> 4, c = idx & 15;
-        const bool ok = (key0 + r) < key_end;
-        const bf16* src = gsrc_rows + (long long)(ok ? (key0 + r) : 0) * DEC_D + c * 8;
-        cp_async_16(dst + swz128(r, c), src, ok);
-    }
+// byte offset of 16-byte chunk `chunk` (0..15 over the 128 head dims) of key row `row` inside one K or V tile made of
+// two 128-B-swizzled TMA boxes ([64 keys][dims 0-63] then [64 keys][dims 64-127])
+__device__ __forceinline__ uint32_t dec_tile_off(int row, int chunk) {
+    return (uint32_t)((chunk >> 3) * DEC_BOX_BYTES + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
 }
 
 __global__ void __launch_bounds__(DEC_THREADS)
-attn_decode_kernel(const DecParams p) {
-    pdl_wait();
+attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const DecParams p) {
     pdl_launch_dependents();
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sQ = smem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;                                        // [STAGES][K lo | K hi | V lo | V hi], 1024-B aligned boxes
+    uint8_t* sQ = smem + DEC_STAGES * DEC_STAGE_BYTES;           // 4 KB
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + 4096); // [STAGES]
+    uint64_t* empty_bar = full_bar + DEC_STAGES;                 // [STAGES]
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    uint8_t* sK = smem + 4096 + warp * 4 * DEC_TILE_BYTES;      // [2][16][128]
-    uint8_t* sV = sK + 2 * DEC_TILE_BYTES;
 
+    // ctx_len / pos were written by the previous step's argmax kernel, which completed before this step's first kernel
+    // could even start, so they may be read ahead of the dependency wait.
     const int ctx = p.ctx_len[b];
     int chunk = (ctx + p.n_splits - 1) / p.n_splits;
-    chunk = (chunk + DEC_TILE * DEC_WARPS - 1) / (DEC_TILE * DEC_WARPS) * (DEC_TILE * DEC_WARPS);
+    chunk = (chunk + DEC_RING_KEYS - 1) / DEC_RING_KEYS * DEC_RING_KEYS;
     const int k_begin = split * chunk;
     const int k_end = min(ctx, k_begin + chunk);
+    const int n_tiles = (k_end > k_begin) ? (k_end - k_begin + DEC_RING_KEYS - 1) / DEC_RING_KEYS : 0;
+    const int row0 = (b * p.n_kv_heads + kvh) * (int)p.ctx_max + k_begin;       // tensor-map row of this CTA's first key
+    // the split whose key range holds key ctx-1, the token appended this step (its cache row is written by this kernel's
+    // fused QKV finalize, or by the predecessor kernel on the unfused path)
+    const bool holds_new = (ctx - 1 >= k_begin) && (ctx - 1 < k_end);
 
-    const bf16* kbase = p.kc + ((long long)b * p.n_kv_heads + kvh) * p.ctx_max * DEC_D;
-    const bf16* vbase = p.vc + ((long long)b * p.n_kv_heads + kvh) * p.ctx_max * DEC_D;
+    if (tid == 0) {
+        for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], DEC_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == DEC_WARPS) {
+        // =============================== TMA producer ===============================
+        // The whole warp follows the control flow (bar.sync must be warp-convergent); lane 0 issues the copies.
+        // The last tile of the split that holds key ctx-1 is written by this very kernel (fused QKV finalize) or by the
+        // predecessor kernel: it waits for the dependency.  Everything older is immutable by now.
+        const int early = holds_new ? n_tiles - 1 : n_tiles;
+        auto issue = [&](int i) {
+            const int st = i % DEC_STAGES;
+            uint8_t* dst = ring + st * DEC_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[st], DEC_STAGE_BYTES);
+            tma_load_2d(dst, &tm_k, 0, row0 + i * DEC_RING_KEYS, &full_bar[st]);
+            tma_load_2d(dst + DEC_BOX_BYTES, &tm_k, 64, row0 + i * DEC_RING_KEYS, &full_bar[st]);
+            tma_load_2d(dst + 2 * DEC_BOX_BYTES, &tm_v, 0, row0 + i * DEC_RING_KEYS, &full_bar[st]);
+            tma_load_2d(dst + 3 * DEC_BOX_BYTES, &tm_v, 64, row0 + i * DEC_RING_KEYS, &full_bar[st]);
+        };
+        int i = 0;
+        if (lane == 0) {
+            prefetch_tensormap(&tm_k); prefetch_tensormap(&tm_v);
+            for (; i < early && i < DEC_STAGES; ++i) issue(i);          // ring-full of immutable tiles ahead of the wait
+        }
+        __syncwarp();
+        pdl_wait();
+        if (p.qkv_partial != nullptr && holds_new) {
+            // the appended k/v row is produced by the consumer warps of this CTA: wait until they published it
+            asm volatile("bar.sync 2, %0;" ::"n"(DEC_THREADS) : "memory");
+        }
+        if (lane == 0) {
+            for (; i < n_tiles; ++i) {
+                if (i >= DEC_STAGES) mbar_wait(&empty_bar[i % DEC_STAGES], ((i / DEC_STAGES) & 1) ^ 1);
+                issue(i);
+            }
+        }
+        return;
+    }
+
+    // =============================== consumer warps ===============================
+    pdl_wait();
 
     // Q tile: rows 0..G-1 = the group's q heads, rows G..15 zero
     if (p.qkv_partial == nullptr) {
         const bf16* qg = p.q + (long long)b * p.n_q_heads * DEC_D + (long long)kvh * p.group * DEC_D;
-        for (int idx = tid; idx < 16 * 16; idx += DEC_THREADS) {
+        for (int idx = tid; idx < 16 * 16; idx += DEC_WARPS * 32) {
             const int r = idx >> 4, c = idx & 15;
             uint4 val = make_uint4(0, 0, 0, 0);
             if (r < p.group) val = *reinterpret_cast<const uint4*>(qg + r * DEC_D + c * 8);
@@ -99,16 +152,16 @@ attn_decode_kernel(const DecParams p) {
         }
     } else {
         // ---- fused QKV finalize: split-K reduce (fixed order) + bias + RoPE; q -> sQ, k/v -> cache row `pos` ----
-        for (int idx = tid; idx < (16 - p.group) * 16; idx += DEC_THREADS) {
+        for (int idx = tid; idx < (16 - p.group) * 16; idx += DEC_WARPS * 32) {
             const int r = p.group + (idx >> 4), c = idx & 15;
             *reinterpret_cast<uint4*>(sQ + swz128(r, c)) = make_uint4(0, 0, 0, 0);
         }
         const int posb = p.pos[b];
-        const bool owns_new = (posb >= k_begin) && (posb < k_end);        // the split whose key range holds the new token
+        const bool owns_new = holds_new;                                   // requires pos[b] == ctx_len[b] - 1
         const int N = (p.n_q_heads + 2 * p.n_kv_heads) * DEC_D;
         const long long sstride = (long long)(gridDim.z) * N;
         const int n_units = (p.group + 2) * 16;                            // (head, 4-column pair chunk)
-        for (int u = tid; u < n_units; u += DEC_THREADS) {
+        for (int u = tid; u < n_units; u += DEC_WARPS * 32) {
             const int hl = u >> 4, c4 = u & 15;
             if (hl >= p.group && !owns_new) continue;
             const int col0 = (hl < p.group ? (kvh * p.group + hl)
@@ -160,7 +213,12 @@ attn_decode_kernel(const DecParams p) {
             }
         }
     }
-    __syncthreads();
+    if (p.qkv_partial != nullptr && holds_new) {
+        asm volatile("fence.proxy.async;" ::: "memory");        // generic-proxy cache writes -> visible to the TMA (async proxy) reads
+        __threadfence();
+        asm volatile("bar.sync 2, %0;" ::"n"(DEC_THREADS) : "memory");      // releases the producer's last tile
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");       // sQ complete (consumer warps only)
     uint32_t qf[8][4];
     {
         const int r = (lane & 7) + 8 * ((lane >> 3) & 1);
@@ -174,34 +232,35 @@ attn_decode_kernel(const DecParams p) {
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
 
-    const int n_tiles_cta = (k_end > k_begin) ? (k_end - k_begin + DEC_TILE - 1) / DEC_TILE : 0;
-    const int my_tiles = (n_tiles_cta > warp) ? (n_tiles_cta - warp + DEC_WARPS - 1) / DEC_WARPS : 0;
-
-    if (my_tiles > 0) {
-        dec_load_tile(sK, kbase, k_begin + warp * DEC_TILE, k_end, lane);
-        dec_load_tile(sV, vbase, k_begin + warp * DEC_TILE, k_end, lane);
-    }
-    cp_async_commit();
-    for (int i = 0; i < my_tiles; ++i) {
-        const int buf = i & 1;
-        const int key0 = k_begin + (warp + i * DEC_WARPS) * DEC_TILE;
-        if (i + 1 < my_tiles) {
-            const int nk = key0 + DEC_WARPS * DEC_TILE;
-            dec_load_tile(sK + (buf ^ 1) * DEC_TILE_BYTES, kbase, nk, k_end, lane);
-            dec_load_tile(sV + (buf ^ 1) * DEC_TILE_BYTES, vbase, nk, k_end, lane);
+    for (int i = 0; i < n_tiles; ++i) {
+        const int stg = i % DEC_STAGES;
+        mbar_wait(&full_bar[stg], (i / DEC_STAGES) & 1);
+        const int key0 = k_begin + i * DEC_RING_KEYS + warp * DEC_TILE;       // this warp's 16 keys of the tile
+        if (key0 >= k_end) {                                                   // warp-uniform: nothing of this slice is visible
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stg]);
+            continue;
         }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();
-        const uint32_t kb = smem_u32(sK) + buf * DEC_TILE_BYTES;
-        const uint32_t vb = smem_u32(sV) + buf * DEC_TILE_BYTES;
+        const uint32_t kb = smem_u32(ring + stg * DEC_STAGE_BYTES);
+        const uint32_t vb = kb + 2 * DEC_BOX_BYTES;
+        if (key0 + DEC_TILE > k_end) {
+            // rows past the last visible key hold whatever the cache stripe contains (possibly NaN bit patterns): zero the V
+            // rows so that P = 0 really contributes 0 (K rows are neutralised by the -inf select below)
+            for (int idx = lane; idx < DEC_TILE * 16; idx += 32) {
+                const int r = idx >> 4, c = idx & 15;
+                if (key0 + r >= k_end)
+                    *reinterpret_cast<uint4*>(ring + stg * DEC_STAGE_BYTES + 2 * DEC_BOX_BYTES + dec_tile_off(warp * DEC_TILE + r, c)) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async_smem();       // these generic-proxy writes precede any later TMA refill of the stage
+            __syncwarp();
+        }
 
         float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             uint32_t bfr[4];
-            const int r = (lane & 7) + 8 * (lane >> 4);
-            ldmatrix_x4(bfr, kb + swz128(r, kk * 2 + ((lane >> 3) & 1)));
+            const int r = warp * DEC_TILE + (lane & 7) + 8 * (lane >> 4);
+            ldmatrix_x4(bfr, kb + dec_tile_off(r, kk * 2 + ((lane >> 3) & 1)));
             mma_bf16_16816(s[0], qf[kk], bfr[0], bfr[1]);
             mma_bf16_16816(s[1], qf[kk], bfr[2], bfr[3]);
         }
@@ -248,20 +307,20 @@ attn_decode_kernel(const DecParams p) {
 #pragma unroll
         for (int dp = 0; dp < 8; ++dp) {
             uint32_t bfr[4];
-            const int r = (lane & 7) + 8 * ((lane >> 3) & 1);
-            ldmatrix_x4_trans(bfr, vb + swz128(r, dp * 2 + (lane >> 4)));
+            const int r = warp * DEC_TILE + (lane & 7) + 8 * ((lane >> 3) & 1);
+            ldmatrix_x4_trans(bfr, vb + dec_tile_off(r, dp * 2 + (lane >> 4)));
             mma_bf16_16816(o[2 * dp], pf, bfr[0], bfr[1]);
             mma_bf16_16816(o[2 * dp + 1], pf, bfr[2], bfr[3]);
         }
         __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stg]);           // this warp is done with its slice of the stage
     }
-    cp_async_wait<0>();
     l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 1);
     l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 2);
 
     // ---- merge the 4 warps (rows g < group only; rows 8..15 are padding) -----------------
-    __syncthreads();                                  // all warps done with their K/V buffers
-    float* sO = reinterpret_cast<float*>(smem + 4096);                  // [4 warps][8 rows][128]
+    asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");   // all consumer warps done with the ring (every TMA tile has landed)
+    float* sO = reinterpret_cast<float*>(ring);                         // [4 warps][8 rows][128]
     float* sML = sO + DEC_WARPS * 8 * DEC_D;                            // [4 warps][8 rows][2]
 #pragma unroll
     for (int nb = 0; nb < 16; ++nb) {
@@ -272,8 +331,8 @@ attn_decode_kernel(const DecParams p) {
         sML[(warp * 8 + g) * 2] = m_run[0];
         sML[(warp * 8 + g) * 2 + 1] = l_run[0];
     }
-    __syncthreads();
-    for (int idx = tid; idx < p.group * DEC_D; idx += DEC_THREADS) {
+    asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");
+    for (int idx = tid; idx < p.group * DEC_D; idx += DEC_WARPS * 32) {
         const int r = idx / DEC_D, c = idx % DEC_D;
         float m = -INFINITY;
 #pragma unroll
@@ -334,8 +393,14 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
         configured = true;
     }
+    // K / V cache layer slice [batch * n_kv_heads * ctx_max, 128] bf16, fetched as [64 keys][64 dims] 128-B-swizzled boxes
+    const unsigned long long rows = (unsigned long long)batch * n_kv_heads * (unsigned long long)p.ctx_max;
+    DOTS_REQUIRE(rows < (1ull << 31), "%s: cache too large for 32-bit key coordinates", who);
+    CUtensorMap tk, tv;
+    if (make_tmap_2d_bf16(&tk, p.kc, rows, DEC_D, DEC_D, DEC_RING_KEYS, 64)) return -4;
+    if (make_tmap_2d_bf16(&tv, p.vc, rows, DEC_D, DEC_D, DEC_RING_KEYS, 64)) return -4;
     dim3 grid(n_splits, n_kv_heads, batch);
-    DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, p));
+    DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, tk, tv, p));
     if (n_splits > 1) {
         DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, p.part_o, p.part_ml, p.out, n_splits));
     }

@@ -234,6 +234,33 @@ class Engine:
         ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
                            st["eos"], st["pad"], st["forced"])
 
+    def _new_decode_state(self, B: int, lens: torch.Tensor, kc, vc, ctx_max: int, N: int, eos_token_id=None, pad_token_id: int = 0,
+                          forced_ids: Optional[torch.Tensor] = None) -> dict:
+        """Every buffer one decode step touches (allocated once per generate; the CUDA graph captures their addresses)."""
+        t = self.cfg.text
+        dev = self.device
+        H = t.hidden_size
+        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, eos=-1 if eos_token_id is None else int(eos_token_id),
+                  pad=int(pad_token_id))
+        pl = st["plan"]
+        max_part = max(pl["qkv"] * (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim, pl["o"] * H, pl["down"] * H)
+        st["partial"] = torch.empty(max_part * B, device=dev, dtype=torch.float32)
+        st["resid"] = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
+        st["normed"] = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
+        st["attn"] = torch.empty((B, t.num_attention_heads * t.head_dim), device=dev, dtype=torch.bfloat16)
+        st["act"] = torch.empty((B, t.intermediate_size), device=dev, dtype=torch.bfloat16)
+        st["logits"] = torch.empty((B, t.vocab_size), device=dev, dtype=torch.bfloat16)
+        st["part_o"] = torch.empty((B, t.num_attention_heads, pl["attn"], t.head_dim), device=dev, dtype=torch.float32)
+        st["part_ml"] = torch.empty((B, t.num_attention_heads, pl["attn"], 2), device=dev, dtype=torch.float32)
+        st["last"] = torch.zeros(B, device=dev, dtype=torch.int64)
+        st["out_ids"] = torch.full((B, N), int(pad_token_id), device=dev, dtype=torch.int64)
+        st["step"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st["pos"] = (lens - 1).to(torch.int32)
+        st["ctx_len"] = lens.to(torch.int32)
+        st["finished"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st["forced"] = forced_ids.to(dev).long().contiguous() if forced_ids is not None else None
+        return st
+
     def decode_weight_bytes(self) -> int:
         """bf16 bytes every decode step must stream: all decoder-layer weights + final norm + lm_head."""
         n = self.final_norm.numel() + self.lm_head.numel()
@@ -297,28 +324,8 @@ class Engine:
         kc, vc = self._alloc_cache(B, ctx_max)
         x = self._prefill(ids_packed, slots, image_embeds, cu, seq_lens, positions, seq_of_tok, kc, vc, ctx_max)
 
-        H = t.hidden_size
-        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, eos=-1 if eos_token_id is None else int(eos_token_id),
-                  pad=int(pad_token_id))
+        st = self._new_decode_state(B, lens, kc, vc, ctx_max, N, eos_token_id, pad_token_id, forced_ids)
         pl = st["plan"]
-        max_part = max(pl["qkv"] * (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim, pl["o"] * H,
-                       pl["gu"] * 2 * t.intermediate_size, pl["down"] * H)
-        st["partial"] = torch.empty(max_part * B, device=dev, dtype=torch.float32)
-        st["resid"] = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
-        st["normed"] = torch.empty((B, H), device=dev, dtype=torch.bfloat16)
-        st["q"] = torch.empty((B, t.num_attention_heads * t.head_dim), device=dev, dtype=torch.bfloat16)
-        st["attn"] = torch.empty_like(st["q"])
-        st["act"] = torch.empty((B, t.intermediate_size), device=dev, dtype=torch.bfloat16)
-        st["logits"] = torch.empty((B, t.vocab_size), device=dev, dtype=torch.bfloat16)
-        st["part_o"] = torch.empty((B, t.num_attention_heads, pl["attn"], t.head_dim), device=dev, dtype=torch.float32)
-        st["part_ml"] = torch.empty((B, t.num_attention_heads, pl["attn"], 2), device=dev, dtype=torch.float32)
-        st["last"] = torch.zeros(B, device=dev, dtype=torch.int64)
-        st["out_ids"] = torch.full((B, N), int(pad_token_id), device=dev, dtype=torch.int64)
-        st["step"] = torch.zeros(B, device=dev, dtype=torch.int32)
-        st["pos"] = (lens - 1).to(torch.int32)
-        st["ctx_len"] = lens.to(torch.int32)
-        st["finished"] = torch.zeros(B, device=dev, dtype=torch.int32)
-        st["forced"] = forced_ids.to(dev).long().contiguous() if forced_ids is not None else None
         all_logits = torch.empty((N, B, t.vocab_size), device=dev, dtype=torch.bfloat16) if return_logits else None
 
         # first token: final norm + lm_head on each sequence's last prompt position
