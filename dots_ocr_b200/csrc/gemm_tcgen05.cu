@@ -42,8 +42,12 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // Decode (swap-AB) kernels keep the ring under half an SM's shared memory so that two CTAs -- usually of two
     // consecutive kernels of the decode step, overlapped by programmatic dependent launch -- stream weights at once.
-    static constexpr int STAGES = SWAP ? (BLOCK_N >= 256 ? 2 : 4) : (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-    static constexpr int MIN_CTAS = (SWAP && BLOCK_N <= 128) ? 2 : 1;
+#ifndef GEMM_SWAP_STAGES
+#define GEMM_SWAP_STAGES 4
+#endif
+    static constexpr int STAGES = SWAP ? (BLOCK_N >= 256 ? 2 : (BLOCK_N >= 128 ? 4 : GEMM_SWAP_STAGES)) : (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int MIN_CTAS_ = (SWAP && BLOCK_N <= 128 && STAGES * STAGE_BYTES <= 100 * 1024) ? 2 : 1;
+    static constexpr int MIN_CTAS = MIN_CTAS_;
     static constexpr int BAR_BYTES = 1024;
     // SWIGLU_T: the up-projection warps hand their bf16-rounded values to the gate warps through shared memory
     static constexpr int XCH_BYTES = (EPI == DOTS_EPI_SWIGLU_T) ? BLOCK_N * 64 * 2 : 0;
