@@ -307,6 +307,19 @@ def decode_swiglu(partial, splits, act):
     _lib.check(rc, "dots_decode_swiglu")
 
 
+def decode_chain(attn, w_o, w_gu, w_down, w_qkv_next, partial, resid, normed, act, ln_mid, ln_next, counters, splits_o: int,
+                 splits_down: int, splits_qkv: int, eps: float):
+    """Persistent per-layer decode kernel: o_proj -> norm -> gate|up+SwiGLU -> down_proj -> norm -> [next layer's qkv]."""
+    B, H = resid.shape
+    inter = act.shape[1]
+    assert counters.dtype == torch.int32 and counters.numel() >= 8 and partial.dtype == torch.float32
+    qkv_n = w_qkv_next.shape[0] if w_qkv_next is not None else 0
+    rc = _lib.load().dots_decode_chain(_p(attn), _p(w_o), _p(w_gu), _p(w_down), _p(w_qkv_next), _p(partial), _p(resid), _p(normed),
+                                       _p(act), _p(ln_mid), _p(ln_next), _p(counters), B, H, inter, qkv_n, attn.shape[1], splits_o,
+                                       splits_down, splits_qkv, C.c_float(eps), _stream())
+    _lib.check(rc, "dots_decode_chain")
+
+
 def set_pdl(enable: bool) -> None:
     """Programmatic dependent launch between consecutive kernels (default on)."""
     _lib.check(_lib.load().dots_set_pdl(int(bool(enable))), "dots_set_pdl")

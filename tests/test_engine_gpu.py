@@ -168,3 +168,21 @@ def test_pdl_on_off_identical(tiny):
     finally:
         ops.set_pdl(True)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+def test_decode_chain_kernel_on_off_identical(tiny):
+    """Decode through the persistent per-layer kernel == decode through one kernel per op (greedy ids and logits)."""
+    cfg, d = tiny
+    ck, eng = d["random"]
+    pv, grid, rows = _inputs(cfg, [(1, 8, 8), (1, 8, 8), (1, 4, 12)][:2])
+    ids = torch.stack(rows)
+    outs = []
+    try:
+        for flag in (False, True):
+            eng.decode_chain = flag
+            o = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=24, return_logits=True, use_graph=False)
+            o2 = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=24)
+            outs.append((o.sequences.cpu(), o.logits.float().cpu(), o2.sequences.cpu()))
+    finally:
+        eng.decode_chain = False
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
