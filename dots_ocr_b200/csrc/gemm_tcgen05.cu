@@ -241,35 +241,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 // swap-AB decode GEMM over the gate|up weight: tile rows 0-63 are gate features, rows 64-127 the matching up
                 // features (warps 0,1 / 2,3 of this group).  Up warps publish bf16(up) through shared memory, gate warps
                 // finish  act[b][f] = bf16( bf16(silu(bf16 g)) * bf16 u )  -- the same rounding points as the prefill epilogue.
+                // All four warps share the SiLU work: gate warps publish bf16(g) of the upper half of the batch tile, up warps
+                // publish bf16(u) of the lower half; then gate warps finish batch columns [0, BN/2) and up warps [BN/2, BN).
                 bf16* out = reinterpret_cast<bf16*>(p.out);
                 const int fl = (wq & 1) * 32 + lane;                 // feature within the 64-block
-                if (wq >= 2) {
+                const bool is_up = wq >= 2;
+                constexpr int HALF = BLOCK_N / 2;
+                static_assert(HALF % 16 == 0, "batch tile halves are read in 16-column TMEM chunks");
+                const int f = m_blk * 64 + fl;
 #pragma unroll 1
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(t_row + c * 32, v);
+                for (int h0 = 0; h0 < HALF; h0 += 32) {              // 32 batch columns of each half per pass (register budget)
+                    constexpr int W = HALF < 32 ? HALF : 32;
+                    float mine[W];
+                    const int pub0 = (is_up ? 0 : HALF) + h0, keep0 = (is_up ? HALF : 0) + h0;
+#pragma unroll
+                    for (int c = 0; c < W / 16; ++c) {
+                        uint32_t v[16];
+                        tmem_ld_32x32b_x16(t_row + pub0 + c * 16, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) xch[(c * 32 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                        for (int j = 0; j < 16; ++j) xch[(pub0 + c * 16 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
                     }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-                if (wq < 2) {
-                    const int f = m_blk * 64 + fl;
-#pragma unroll 1
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(t_row + c * 32, v);
-                        tmem_ld_wait();
-                        if (f < p.M / 2) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int b = n_blk * BLOCK_N + c * 32 + j;
-                                if (b < p.N) {
-                                    const float gv = bf16_round(__uint_as_float(v[j]));
-                                    const float uv = __bfloat162float(xch[(c * 32 + j) * 64 + fl]);
-                                    out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
-                                }
+                    for (int c = 0; c < W / 16; ++c) {
+                        uint32_t v[16];
+                        tmem_ld_32x32b_x16(t_row + keep0 + c * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mine[c * 16 + j] = __uint_as_float(v[j]);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+                    if (f < p.M / 2) {
+#pragma unroll
+                        for (int j = 0; j < W; ++j) {
+                            const int b = n_blk * BLOCK_N + keep0 + j;
+                            if (b < p.N) {
+                                const float other = __bfloat162float(xch[(keep0 + j) * 64 + fl]);
+                                const float gv = is_up ? other : bf16_round(mine[j]);
+                                const float uv = is_up ? bf16_round(mine[j]) : other;
+                                out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
                             }
                         }
                     }
