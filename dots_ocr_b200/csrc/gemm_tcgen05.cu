@@ -19,7 +19,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;        // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;      // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue groups
+constexpr int EPI_GROUPS = 2;          // each group = 4 warps (one per TMEM lane quarter) handling half of the tile's columns
 
 struct GemmParams {
     int M, N, K;                   // rows of A, rows of B, reduction length
@@ -99,7 +100,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);            // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], 4 * EPI_GROUPS);   // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -200,6 +201,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ===================== epilogue =====================
         pdl_wait();                                          // residual / bias reads and all output writes follow the dependency
         const int wq = warp & 3;                             // TMEM lane quarter this warp may read
+        const int eg = (warp - 4) >> 2;                      // epilogue group: which half of the tile's columns
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -215,7 +217,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 static_assert(EPI != DOTS_EPI_SWIGLU || BLOCK_N == 256, "swiglu epilogue needs BLOCK_N=256");
                 bf16* out = reinterpret_cast<bf16*>(p.out);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = eg * 2; c < eg * 2 + 2; ++c) {
                     uint32_t g[32], u[32];
                     tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + (c & 1) * 32, g);
                     tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + 64 + (c & 1) * 32, u);
@@ -241,6 +243,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 // swap-AB decode GEMM over the gate|up weight: tile rows 0-63 are gate features, rows 64-127 the matching up
                 // features (warps 0,1 / 2,3 of this group).  Up warps publish bf16(up) through shared memory, gate warps
                 // finish  act[b][f] = bf16( bf16(silu(bf16 g)) * bf16 u )  -- the same rounding points as the prefill epilogue.
+                // (epilogue group 0 only: the exchange below is a 4-warp named barrier)
+                if (eg == 0) {
                 // All four warps share the SiLU work: gate warps publish bf16(g) of the upper half of the batch tile, up warps
                 // publish bf16(u) of the lower half; then gate warps finish batch columns [0, BN/2) and up warps [BN/2, BN).
                 bf16* out = reinterpret_cast<bf16*>(p.out);
@@ -285,12 +289,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // xch is free for the next tile
+                }
             } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
                 // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
                 // partial[split][b][feature] fp32; lanes write consecutive features (coalesced).
                 float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
@@ -307,7 +312,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 bf16* out = reinterpret_cast<bf16*>(p.out);
                 const float bias_v = (p.bias != nullptr && row < p.M) ? __bfloat162float(p.bias[row]) : 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
@@ -326,7 +331,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 bf16* out = reinterpret_cast<bf16*>(p.out);
                 const bool row_ok = row < p.M;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                for (int c = eg * (BLOCK_N / 64); c < (eg + 1) * (BLOCK_N / 64); c += 2) {
                     uint32_t v[2][32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v[0]);
                     tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[1]);
