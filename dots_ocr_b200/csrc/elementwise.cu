@@ -393,30 +393,25 @@ __global__ void __launch_bounds__(1024) argmax_advance_kernel(const bf16* __rest
 // acc[0..7] += sum over splits of 8 consecutive fp32 at p0 + s * sstride, in split order (deterministic), with four
 // independent 32-byte loads in flight per thread.
 __device__ __forceinline__ void sum_splits8(const float* __restrict__ p0, long long sstride, int splits, float (&acc)[8]) {
-    int s = 0;
-    for (; s + 4 <= splits; s += 4) {
-        float4 a[4], d[4];
+    // up to 16 splits: every 32-byte load is issued before the first add (one L2 round trip); adds stay in split order
+    for (int s0 = 0; s0 < splits; s0 += 16) {
+        float4 a[16], d[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4* ps = reinterpret_cast<const float4*>(p0 + (s + u) * sstride);
-            a[u] = ps[0]; d[u] = ps[1];
+        for (int u = 0; u < 16; ++u) {
+            if (s0 + u < splits) {
+                const float4* ps = reinterpret_cast<const float4*>(p0 + (s0 + u) * sstride);
+                a[u] = ps[0]; d[u] = ps[1];
+            }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
-            acc[4] += d[u].x; acc[5] += d[u].y; acc[6] += d[u].z; acc[7] += d[u].w;
+        for (int u = 0; u < 16; ++u) {
+            if (s0 + u < splits) {
+                acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+                acc[4] += d[u].x; acc[5] += d[u].y; acc[6] += d[u].z; acc[7] += d[u].w;
+            }
         }
-    }
-    for (; s < splits; ++s) {
-        const float4* ps = reinterpret_cast<const float4*>(p0 + s * sstride);
-        const float4 a = ps[0], d = ps[1];
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-        acc[4] += d.x; acc[5] += d.y; acc[6] += d.z; acc[7] += d.w;
     }
 }
-
-// All take split-K partial sums [splits][B][N] fp32 from dots_gemm_skinny_bf16 and reduce them in a
-// fixed order (deterministic), then apply the HF rounding points.
 
 // x = embed[last_id]; resid = x; normed = RMSNorm(x) * w          (one warp per sequence)
 __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table,
