@@ -1,21 +1,22 @@
 // Variable-length fused attention forward on the 5th-gen tensor cores (head_dim 128).
 //
-// One CTA owns TWO 128-row query tiles ("chains" 0 and 1) of one (sequence, head).  Keys/values arrive in 64-key tiles.
-// Per chain the score tile S is DOUBLE-BUFFERED in TMEM, so S(j+1) = Q K_{j+1}^T is computed while the softmax warps
-// still work on S(j); the only true dependency left on the tensor pipe is P(j) -> O += P(j) V_j:
+// One CTA owns TWO 128-row query tiles ("chains" 0 and 1) of one (sequence, head); the chains are independent dependency
+// chains (S -> softmax -> P -> O), so the tensor pipe works on one while the other is in its softmax:
 //
-//   warp 0        TMA producer: Q_0, Q_1 once; K_j / V_j tiles (64 keys) through 4-deep mbarrier rings
-//   warp 1        tcgen05.mma issuer:  S_t(j) = Q_t K_j^T   (SS, 128x64x16 x 8)
-//                                      O_t  += P_t(j) V_j   (TS: P read from TMEM, V MN-major in smem, 128x128x16 x 4)
-//                 program order per chain:  S(0) S(1) | wait P(j): PV(j), S(j+2) | ...
+//   warp 0        TMA producer: Q_0, Q_1 once; K_j / V_j tiles through mbarrier rings (128-B swizzle boxes)
+//   warp 1 / 2    tcgen05.mma issuers, one per chain (the warp runs the control flow convergently, one elected lane issues):
+//                     S_t(j) = Q_t K_j^T   (SS: both operands in shared memory)
+//                     O_t  += P_t(j) V_j   (TS: P read from TMEM, V MN-major in shared memory)
 //   warps 4-7     softmax warpgroup of chain 0  (thread = query row = TMEM lane)
 //   warps 8-11    softmax warpgroup of chain 1
 //
-// TMEM (512 columns): chain t at t*256: S buffer 0 [0,64)  S buffer 1 [64,128)  O [128,256).  P(j) (bf16 pairs) overwrites
-// the first 32 columns of the S buffer it came from.  Softmax is fp32 in the exp2 domain with packed fp32x2 arithmetic;
-// the running max only advances when it grows by more than 2^8 (lazy rescale), so O in TMEM is rarely touched by the
-// softmax warps (and when it is, they first wait for P(j-1) V to retire).  P is rounded to bf16 before P*V, the row sum
-// accumulates the unrounded fp32 values (flash_attention_2's rounding points).
+// Two tilings (FA_BN_KEYS): 128-key tiles with one S buffer per chain (default: S(j+1) is issued right behind P(j) V_j), or
+// 64-key tiles with S double-buffered in TMEM (S(j+1) computed during softmax(j)); measured 1107/1235 vs 1042/1150 TFLOP/s at
+// L = 5476 / 19600.  TMEM (512 columns): chain t at t*256: S [0,128) (or two 64-column buffers), O [128,256).  P(j) (bf16
+// pairs) overwrites the first half of the S buffer it came from.  Softmax is fp32 in the exp2 domain with packed fp32x2
+// arithmetic; the running max only advances when it grows by more than 2^8 (lazy rescale), so O in TMEM is rarely touched
+// by the softmax warps.  P is rounded to bf16 before P*V, the row sum accumulates the unrounded fp32 values
+// (flash_attention_2's rounding points).
 //
 // SURVEY.md §8a rows a10 (ViT, bidirectional, one segment per image) and a19 (LLM prefill, causal GQA).
 #include "common.h"
@@ -26,12 +27,17 @@ namespace dots {
 
 constexpr int FA_D = 128;
 constexpr int FA_BM = 128;          // rows per query tile (two tiles per CTA)
-constexpr int FA_BN = 64;           // keys per KV tile
+#ifndef FA_BN_KEYS
+#define FA_BN_KEYS 128
+#endif
+constexpr int FA_BN = FA_BN_KEYS;   // keys per KV tile: 64 (S double-buffered in TMEM) or 128 (one S buffer per chain)
+constexpr int FA_SBUF = (FA_BN == 64) ? 2 : 1;      // S buffers per chain (TMEM: 2 x 64 or 1 x 128 columns)
+static_assert(FA_BN == 64 || FA_BN == 128, "FA_BN_KEYS must be 64 or 128");
 constexpr int FA_THREADS = 384;
 constexpr int FA_QTILE_BYTES = FA_BM * FA_D * 2;     // 32 KB = two [128 x 64] swizzle boxes
 constexpr int FA_KVTILE_BYTES = FA_BN * FA_D * 2;    // 16 KB = two [64 x 64] swizzle boxes
-constexpr int FA_KSTAGES = 4;
-constexpr int FA_VSTAGES = 4;
+constexpr int FA_KSTAGES = (FA_BN == 64) ? 4 : 3;
+constexpr int FA_VSTAGES = (FA_BN == 64) ? 4 : 2;
 constexpr int FA_SMEM = 2 * FA_QTILE_BYTES + (FA_KSTAGES + FA_VSTAGES) * FA_KVTILE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
 
 struct FaParams {
@@ -97,6 +103,10 @@ __device__ __forceinline__ void ex2_poly_f32x2(uint64_t x2, float& p0, float& p1
 #define FA_EMU_MASK 0u               // bit i set: packed pair i of the 32 pairs of a row takes the polynomial path
 #endif
 
+// S buffer (and its barrier) used by key tile j, and the parity of that barrier's phase for tile j
+__device__ __forceinline__ constexpr int fa_buf(int j) { return FA_SBUF == 2 ? (j & 1) : 0; }
+__device__ __forceinline__ constexpr uint32_t fa_par(int j) { return (uint32_t)(FA_SBUF == 2 ? ((j >> 1) & 1) : (j & 1)); }
+
 template <bool CAUSAL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -151,7 +161,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     if (*tmem_ptr != 0u) __trap();
     constexpr uint32_t tmem_base = 0u;
 
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");   // 128 x (168 - 96) released >= 256 x (200 - 168) acquired
+    // register hand-over: 128 x (168 - dec) released >= 256 x (inc - 168) acquired
+    if (warp < 4) {
+        if (FA_BN == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    }
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
@@ -195,10 +209,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             const uint64_t dk0 = umma_desc_k_sw128(smem_u32(sK));
             const uint64_t dv0 = umma_desc_mn_sw128(smem_u32(sV), FA_KVTILE_BYTES / 2, 1024);
             auto issue_s = [&](int t, int j) {
-                const uint32_t tS = tmem_base + t * 256 + (j & 1) * 64;
+                const uint32_t tS = tmem_base + t * 256 + fa_buf(j) * 64;
                 const uint64_t dq = dq0 + (uint64_t)(t * (FA_QTILE_BYTES >> 4));
                 const uint64_t dk = dk0 + (uint64_t)((j % FA_KSTAGES) * (FA_KVTILE_BYTES >> 4));
-                uint64_t* bar = &s_full[t * 2 + (j & 1)];
+                uint64_t* bar = &s_full[t * 2 + fa_buf(j)];
                 if (leader) {
 #ifndef FA_DBG_NOS
 #pragma unroll
@@ -213,11 +227,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 __syncwarp();
             };
             auto issue_pv = [&](int t, int j) {
-                const uint32_t tP = tmem_base + t * 256 + (j & 1) * 64;
+                const uint32_t tP = tmem_base + t * 256 + fa_buf(j) * 64;
                 const uint32_t tO = tmem_base + t * 256 + 128;
                 const uint64_t dv = dv0 + (uint64_t)((j % FA_VSTAGES) * (FA_KVTILE_BYTES >> 4));
                 const uint32_t acc0 = (j == 0) ? 0u : 1u;
-                uint64_t* bar = &pv_done[t * 2 + (j & 1)];
+                uint64_t* bar = &pv_done[t * 2 + fa_buf(j)];
                 if (leader) {
 #ifndef FA_DBG_NOPV
 #pragma unroll
@@ -236,27 +250,29 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             };
 
             mbar_wait(q_full, 0);
-            for (int jj = 0; jj < 2 && jj < n_kv_u; ++jj) {
+            for (int jj = 0; jj < FA_SBUF && jj < n_kv_u; ++jj) {
                 mbar_wait(&k_full[jj % FA_KSTAGES], 0);
                 tc_fence_after();
                 issue_s(t, jj);
                 commit(&k_empty[jj % FA_KSTAGES]);
             }
             for (int j = 0; j < n_kv_u; ++j) {
-                const bool more = (j + 2 < n_kv_u);
+                const int jn = j + FA_SBUF;                 // the S tile that reuses the buffer P_t(j) lives in
+                const bool more = (jn < n_kv_u);
                 mbar_wait(&v_full[j % FA_VSTAGES], (j / FA_VSTAGES) & 1);
-                if (more) mbar_wait(&k_full[(j + 2) % FA_KSTAGES], ((j + 2) / FA_KSTAGES) & 1);
-                mbar_wait(&p_full[t * 2 + (j & 1)], (j >> 1) & 1);
+                if (more) mbar_wait(&k_full[jn % FA_KSTAGES], (jn / FA_KSTAGES) & 1);
+                mbar_wait(&p_full[t * 2 + fa_buf(j)], fa_par(j));
                 tc_fence_after();
                 issue_pv(t, j);
-                if (more) issue_s(t, j + 2);                // overwrites buffer j&1: ordered after P_t(j) V_j (same issuing thread)
+                if (more) issue_s(t, jn);                   // overwrites that buffer: ordered after P_t(j) V_j (same issuing thread)
                 commit(&v_empty[j % FA_VSTAGES]);
-                if (more) commit(&k_empty[(j + 2) % FA_KSTAGES]);
+                if (more) commit(&k_empty[jn % FA_KSTAGES]);
             }
         }
     } else if (warp >= 4) {
         // =============================== softmax warpgroups ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        if (FA_BN == 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         const int t = (warp - 4) >> 2;                   // chain
         const int wq = warp & 3;                         // TMEM lane quarter
         const int row = wq * 32 + lane;                  // row within the tile == TMEM lane
@@ -267,17 +283,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         float m_run = -INFINITY;                         // running max in raw score units
         float l_run = 0.f;
         for (int j = 0; j < n_kv; ++j) {
-            const uint32_t tS = tSbase + (j & 1) * 64;
-            mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
+            const uint32_t tS = tSbase + fa_buf(j) * 64;
+            mbar_wait(&s_full[t * 2 + fa_buf(j)], fa_par(j));
             tc_fence_after();
 #ifdef FA_DBG_NOSOFTMAX
             tc_fence_before();
-            mbar_arrive(&p_full[t * 2 + (j & 1)]);
+            mbar_arrive(&p_full[t * 2 + fa_buf(j)]);
             continue;
 #endif
             float s[FA_BN];
-            tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-            tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+#pragma unroll
+            for (int c = 0; c < FA_BN / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
             tmem_ld_wait();
             const int k0 = j * FA_BN;
             const bool need_mask = (k0 + FA_BN > L) || (CAUSAL && (k0 + FA_BN - 1 > q0 + t * FA_BM + wq * 32));
@@ -305,7 +321,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                     // O_t must hold every product issued so far: S_t(j) ready only implies P(j-2) V retired, so wait for
                     // P(j-1) V explicitly.  Its barrier is in one of two states (that phase pending / complete): skipping
                     // this wait on other iterations cannot alias the parity.
-                    mbar_wait(&pv_done[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+                    // (with a single S buffer S_t(j) was issued behind P(j-1) V, so it has retired already)
+                    if (FA_SBUF == 2) mbar_wait(&pv_done[t * 2 + fa_buf(j - 1)], fa_par(j - 1));
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -324,22 +341,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             // p = exp2(s * scale - m * scale): packed fp32x2 FMA / add (FFMA2, FADD2); four independent packed row-sum accumulators
             const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), mn2 = pack_f32x2(mneg, mneg);
             uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
-            uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const uint64_t x2 = ffma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), sc2, mn2);
-                float p0, p1;
-                if ((FA_EMU_MASK >> i) & 1u) {
-                    ex2_poly_f32x2(x2, p0, p1);
-                } else {
-                    float x0, x1;
-                    unpack_f32x2(x2, x0, x1);
-                    p0 = ex2f(x0); p1 = ex2f(x1);
+            for (int c = 0; c < FA_BN / 64; ++c) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint64_t x2 = ffma_f32x2(pack_f32x2(s[c * 64 + 2 * i], s[c * 64 + 2 * i + 1]), sc2, mn2);
+                    float p0, p1;
+                    if ((FA_EMU_MASK >> i) & 1u) {
+                        ex2_poly_f32x2(x2, p0, p1);
+                    } else {
+                        float x0, x1;
+                        unpack_f32x2(x2, x0, x1);
+                        p0 = ex2f(x0); p1 = ex2f(x1);
+                    }
+                    acc2[i & 3] = fadd_f32x2(acc2[i & 3], pack_f32x2(p0, p1));
+                    pk[i] = pack_bf16x2(p0, p1);
                 }
-                acc2[i & 3] = fadd_f32x2(acc2[i & 3], pack_f32x2(p0, p1));
-                pk[i] = pack_bf16x2(p0, p1);
+                tmem_st_32x32b_x32(tS + c * 32, pk);
             }
-            tmem_st_32x32b_x32(tS, pk);
             {
                 float a0, a1, b0, b1;
                 unpack_f32x2(fadd_f32x2(acc2[0], acc2[1]), a0, a1);
@@ -348,10 +368,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&p_full[t * 2 + (j & 1)]);
+            mbar_arrive(&p_full[t * 2 + fa_buf(j)]);
         }
         // ---- epilogue: O_t / l -> bf16 -> global ------------------------------------------
-        mbar_wait(&pv_done[t * 2 + ((n_kv - 1) & 1)], ((n_kv - 1) >> 1) & 1);
+        mbar_wait(&pv_done[t * 2 + fa_buf(n_kv - 1)], fa_par(n_kv - 1));
         tc_fence_after();
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
         bf16* dst = p.o + (long long)(tok0 + qi) * p.os + head * FA_D;

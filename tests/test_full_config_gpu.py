@@ -57,6 +57,39 @@ def test_full_size_single_page_matches_hf_bf16():
     assert torch.equal(got_ids, ref_ids), (got_ids[0, -N:].tolist(), ref_ids[0, -N:].tolist())
 
 
+def test_full_size_logits_random_weights():
+    """Pre-sampling logits at the real dimensions, N(0, 0.02) weights (no peaked head), teacher-forced on the oracle's ids:
+    max |engine - HF bf16| <= 0.06 sigma(logits), the tolerance stated in tests/test_engine_gpu.py."""
+    from dots_ocr_b200 import config, weights
+    from dots_ocr_b200.engine import Engine
+    from dots_ocr_b200.utils.image_utils import vit_grid, token_counts
+    from oracle.model import DotsOracle
+    cfg = config.full()
+    ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=DEV)
+    gh, gw = vit_grid(1024, 1024)
+    s_vit, t_img = token_counts(1024, 1024, patch=cfg.vision.patch_size, merge=cfg.vision.spatial_merge_size)
+    g = torch.Generator().manual_seed(99)
+    pv = torch.randn(s_vit, cfg.vision.patch_dim, generator=g)
+    grid = torch.tensor([[1, gh, gw]])
+    txt = torch.randint(0, 151643, (64,), generator=g)
+    ids = torch.cat([txt[:32], torch.full((t_img,), cfg.image_token_id), txt[32:]]).unsqueeze(0)
+    N = 4
+    orc = DotsOracle(cfg, ck, torch.bfloat16, DEV)
+    ref_ids = orc.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N).cpu()
+    new = ref_ids[:, ids.shape[1]:]
+    ref_logits = orc.teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()            # [1, N, V] fp32 view of bf16 logits
+    del orc
+    torch.cuda.empty_cache()
+    eng = Engine(cfg, ck, DEV)
+    out = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N, forced_ids=new, return_logits=True)
+    got = out.logits.float().cpu()
+    sd = float(ref_logits.std())
+    err = float((got - ref_logits).abs().max()) / sd
+    print(f"full-size logits: max |engine - HF bf16| = {err:.4f} sigma")
+    assert got.shape == ref_logits.shape == (1, N, cfg.text.vocab_size)
+    assert err < 6e-2, err
+
+
 def test_attention_tc_long_sequence_cross_check():
     """L = 19600 (configs[4]): O(L^2) fp32 reference is too large; cross-check the two independent kernels instead."""
     from dots_ocr_b200 import ops
