@@ -251,6 +251,8 @@ def run_gpu(args):
         ops.ATTN_IMPL = args.attn_impl
     if args.no_pdl:
         ops.set_pdl(False)
+    if args.gemm_pair is not None:
+        ops.set_gemm_pair(bool(args.gemm_pair))
     cfg = config.PRESETS[args.preset]()
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev)
     eng = Engine(cfg, ck, dev)
@@ -387,6 +389,8 @@ def main():
     ap.add_argument("--preset", default="full")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--gemm-pair", dest="gemm_pair", type=int, default=None, choices=[0, 1],
+                    help="CTA-pair (cta_group::2) kernel for the large prefill GEMMs (default: the library default)")
     ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
     ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "mma"])
     args = ap.parse_args()

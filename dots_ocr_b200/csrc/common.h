@@ -56,6 +56,22 @@ inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// Same, for kernels launched as clusters of `cluster_x` CTAs (CTA pairs for cta_group::2 tensor-core work).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, unsigned cluster_x,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && g_pdl) ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // 2-D bf16 row-major tensor [rows, cols] with row pitch ld (elements) -> TMA map with a
 // {64 x box_rows} box and 128-byte swizzle.  Returns 0 on success.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,

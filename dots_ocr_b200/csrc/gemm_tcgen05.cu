@@ -67,6 +67,201 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_b
     m_blk = r / p.n_blocks;
 }
 
+// Epilogue of one accumulator tile, executed by one epilogue thread: `row` = output row of this thread (TMEM lane),
+// `t_row` = TMEM address of its accumulator row, `eg` = epilogue group (which half of the tile's columns), `m_blk` = tile row
+// index in units of BLOCK_M (swap-AB epilogues only).  Shared by the 1-CTA and the 2-CTA kernels.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int row, int m_blk, int n_blk, int split, uint32_t t_row, int eg,
+                                                   int wq, int lane, bf16* xch) {
+    if constexpr (EPI == DOTS_EPI_SWIGLU) {
+        // B rows are interleaved per 128-block: [64 gate rows | 64 up rows]; out has N/2 columns.
+        static_assert(EPI != DOTS_EPI_SWIGLU || BLOCK_N == 256, "swiglu epilogue needs BLOCK_N=256");
+        bf16* out = reinterpret_cast<bf16*>(p.out);
+#pragma unroll 1
+        for (int c = eg * 2; c < eg * 2 + 2; ++c) {
+            uint32_t g[32], u[32];
+            tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + (c & 1) * 32, g);
+            tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + 64 + (c & 1) * 32, u);
+            tmem_ld_wait();
+            const int col = n_blk * 128 + c * 32;
+            if (row < p.M) {
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float g0 = bf16_round(__uint_as_float(g[2 * j])), g1 = bf16_round(__uint_as_float(g[2 * j + 1]));
+                    float u0 = bf16_round(__uint_as_float(u[2 * j])), u1 = bf16_round(__uint_as_float(u[2 * j + 1]));
+                    float a0 = bf16_round(silu_f(g0)), a1 = bf16_round(silu_f(g1));
+                    o[j] = pack_bf16x2(a0 * u0, a1 * u1);
+                }
+                bf16* dst = out + (long long)row * p.ldo + col;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (col + q * 8 + 8 <= p.N / 2)
+                        *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            }
+        }
+    } else if constexpr (EPI == DOTS_EPI_SWIGLU_T) {
+        // swap-AB decode GEMM over the gate|up weight: tile rows 0-63 are gate features, rows 64-127 the matching up
+        // features (warps 0,1 / 2,3 of this group).  Up warps publish bf16(up) through shared memory, gate warps
+        // finish  act[b][f] = bf16( bf16(silu(bf16 g)) * bf16 u )  -- the same rounding points as the prefill epilogue.
+        // (epilogue group 0 only: the exchange below is a 4-warp named barrier)
+        if (eg == 0) {
+        // All four warps share the SiLU work: gate warps publish bf16(g) of the upper half of the batch tile, up warps
+        // publish bf16(u) of the lower half; then gate warps finish batch columns [0, BN/2) and up warps [BN/2, BN).
+        bf16* out = reinterpret_cast<bf16*>(p.out);
+        const int fl = (wq & 1) * 32 + lane;                 // feature within the 64-block
+        const bool is_up = wq >= 2;
+        constexpr int HALF = BLOCK_N / 2;
+        static_assert(HALF % 16 == 0, "batch tile halves are read in 16-column TMEM chunks");
+        const int f = m_blk * 64 + fl;
+#pragma unroll 1
+        for (int h0 = 0; h0 < HALF; h0 += 32) {              // 32 batch columns of each half per pass (register budget)
+            constexpr int W = HALF < 32 ? HALF : 32;
+            float mine[W];
+            const int pub0 = (is_up ? 0 : HALF) + h0, keep0 = (is_up ? HALF : 0) + h0;
+#pragma unroll
+            for (int c = 0; c < W / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_row + pub0 + c * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xch[(pub0 + c * 16 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+#pragma unroll
+            for (int c = 0; c < W / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_row + keep0 + c * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mine[c * 16 + j] = __uint_as_float(v[j]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+            if (f < p.M / 2) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const int b = n_blk * BLOCK_N + keep0 + j;
+                    if (b < p.N) {
+                        const float other = __bfloat162float(xch[(keep0 + j) * 64 + fl]);
+                        const float gv = is_up ? other : bf16_round(mine[j]);
+                        const float uv = is_up ? bf16_round(mine[j]) : other;
+                        out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
+                    }
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // xch is free for the next tile
+        }
+    } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
+        // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
+        // partial[split][b][feature] fp32; lanes write consecutive features (coalesced).
+        float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+        for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int b = n_blk * BLOCK_N + c * 32 + j;
+                    if (b < p.N) out[((long long)split * p.N + b) * p.ldo + row] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    } else if constexpr (EPI == DOTS_EPI_BF16_T) {
+        // swap-AB, no split: out[b][feature] = bf16(acc + bias[feature]); lanes = consecutive features.
+        bf16* out = reinterpret_cast<bf16*>(p.out);
+        const float bias_v = (p.bias != nullptr && row < p.M) ? __bfloat162float(p.bias[row]) : 0.f;
+#pragma unroll 1
+        for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int b = n_blk * BLOCK_N + c * 32 + j;
+                    if (b < p.N) out[(long long)b * p.ldo + row] = __float2bfloat16_rn(__uint_as_float(v[j]) + bias_v);
+                }
+            }
+        }
+    } else {
+        // Two 32-column chunks per iteration: both TMEM loads and (for the residual epilogue) all eight 16-byte
+        // residual loads are issued before the first use, so one iteration pays one memory latency, not two.
+        static_assert(BLOCK_N % 64 == 0, "generic epilogue walks the tile in 64-column steps");
+        bf16* out = reinterpret_cast<bf16*>(p.out);
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c = eg * (BLOCK_N / 64); c < (eg + 1) * (BLOCK_N / 64); c += 2) {
+            uint32_t v[2][32];
+            tmem_ld_32x32b_x32(t_row + c * 32, v[0]);
+            tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[1]);
+            const int col0 = n_blk * BLOCK_N + c * 32;
+            uint4 rres[2][4];
+            if constexpr (EPI == DOTS_EPI_RESIDUAL) {
+                const bf16* rsrc = p.res + (long long)row * p.ldr + col0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        rres[h][q] = (row_ok && col0 + h * 32 + q * 8 + 8 <= p.N)
+                                         ? *reinterpret_cast<const uint4*>(rsrc + h * 32 + q * 8) : make_uint4(0, 0, 0, 0);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = col0 + h * 32;
+                if (!(row_ok && col < p.N)) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[h][j]);
+                if constexpr (EPI == DOTS_EPI_BIAS || EPI == DOTS_EPI_BIAS_GELU) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (col + q * 8 + 8 <= p.N) {
+                            uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col + q * 8));
+                            f[q * 8 + 0] += bf16_lo(b.x); f[q * 8 + 1] += bf16_hi(b.x);
+                            f[q * 8 + 2] += bf16_lo(b.y); f[q * 8 + 3] += bf16_hi(b.y);
+                            f[q * 8 + 4] += bf16_lo(b.z); f[q * 8 + 5] += bf16_hi(b.z);
+                            f[q * 8 + 6] += bf16_lo(b.w); f[q * 8 + 7] += bf16_hi(b.w);
+                        }
+                    }
+                }
+                if constexpr (EPI == DOTS_EPI_BIAS_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(bf16_round(f[j]));
+                }
+                if constexpr (EPI == DOTS_EPI_RESIDUAL) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 r = rres[h][q];
+                        f[q * 8 + 0] = bf16_round(f[q * 8 + 0]) + bf16_lo(r.x);
+                        f[q * 8 + 1] = bf16_round(f[q * 8 + 1]) + bf16_hi(r.x);
+                        f[q * 8 + 2] = bf16_round(f[q * 8 + 2]) + bf16_lo(r.y);
+                        f[q * 8 + 3] = bf16_round(f[q * 8 + 3]) + bf16_hi(r.y);
+                        f[q * 8 + 4] = bf16_round(f[q * 8 + 4]) + bf16_lo(r.z);
+                        f[q * 8 + 5] = bf16_round(f[q * 8 + 5]) + bf16_hi(r.z);
+                        f[q * 8 + 6] = bf16_round(f[q * 8 + 6]) + bf16_lo(r.w);
+                        f[q * 8 + 7] = bf16_round(f[q * 8 + 7]) + bf16_hi(r.w);
+                    }
+                }
+                bf16* dst = out + (long long)row * p.ldo + col;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (col + q * 8 + 8 <= p.N) {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                        o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                        o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                        o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                        *reinterpret_cast<uint4*>(dst + q * 8) = o;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, GemmSmem<BLOCK_N, EPI>::MIN_CTAS)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -212,193 +407,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int row = m_blk * BLOCK_M + wq * 32 + lane;          // row of A this thread owns
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
 
-            if constexpr (EPI == DOTS_EPI_SWIGLU) {
-                // B rows are interleaved per 128-block: [64 gate rows | 64 up rows]; out has N/2 columns.
-                static_assert(EPI != DOTS_EPI_SWIGLU || BLOCK_N == 256, "swiglu epilogue needs BLOCK_N=256");
-                bf16* out = reinterpret_cast<bf16*>(p.out);
-#pragma unroll 1
-                for (int c = eg * 2; c < eg * 2 + 2; ++c) {
-                    uint32_t g[32], u[32];
-                    tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + (c & 1) * 32, g);
-                    tmem_ld_32x32b_x32(t_row + (c >> 1) * 128 + 64 + (c & 1) * 32, u);
-                    tmem_ld_wait();
-                    const int col = n_blk * 128 + c * 32;
-                    if (row < p.M) {
-                        uint32_t o[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float g0 = bf16_round(__uint_as_float(g[2 * j])), g1 = bf16_round(__uint_as_float(g[2 * j + 1]));
-                            float u0 = bf16_round(__uint_as_float(u[2 * j])), u1 = bf16_round(__uint_as_float(u[2 * j + 1]));
-                            float a0 = bf16_round(silu_f(g0)), a1 = bf16_round(silu_f(g1));
-                            o[j] = pack_bf16x2(a0 * u0, a1 * u1);
-                        }
-                        bf16* dst = out + (long long)row * p.ldo + col;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (col + q * 8 + 8 <= p.N / 2)
-                                *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                    }
-                }
-            } else if constexpr (EPI == DOTS_EPI_SWIGLU_T) {
-                // swap-AB decode GEMM over the gate|up weight: tile rows 0-63 are gate features, rows 64-127 the matching up
-                // features (warps 0,1 / 2,3 of this group).  Up warps publish bf16(up) through shared memory, gate warps
-                // finish  act[b][f] = bf16( bf16(silu(bf16 g)) * bf16 u )  -- the same rounding points as the prefill epilogue.
-                // (epilogue group 0 only: the exchange below is a 4-warp named barrier)
-                if (eg == 0) {
-                // All four warps share the SiLU work: gate warps publish bf16(g) of the upper half of the batch tile, up warps
-                // publish bf16(u) of the lower half; then gate warps finish batch columns [0, BN/2) and up warps [BN/2, BN).
-                bf16* out = reinterpret_cast<bf16*>(p.out);
-                const int fl = (wq & 1) * 32 + lane;                 // feature within the 64-block
-                const bool is_up = wq >= 2;
-                constexpr int HALF = BLOCK_N / 2;
-                static_assert(HALF % 16 == 0, "batch tile halves are read in 16-column TMEM chunks");
-                const int f = m_blk * 64 + fl;
-#pragma unroll 1
-                for (int h0 = 0; h0 < HALF; h0 += 32) {              // 32 batch columns of each half per pass (register budget)
-                    constexpr int W = HALF < 32 ? HALF : 32;
-                    float mine[W];
-                    const int pub0 = (is_up ? 0 : HALF) + h0, keep0 = (is_up ? HALF : 0) + h0;
-#pragma unroll
-                    for (int c = 0; c < W / 16; ++c) {
-                        uint32_t v[16];
-                        tmem_ld_32x32b_x16(t_row + pub0 + c * 16, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) xch[(pub0 + c * 16 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
-                    }
-#pragma unroll
-                    for (int c = 0; c < W / 16; ++c) {
-                        uint32_t v[16];
-                        tmem_ld_32x32b_x16(t_row + keep0 + c * 16, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) mine[c * 16 + j] = __uint_as_float(v[j]);
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-                    if (f < p.M / 2) {
-#pragma unroll
-                        for (int j = 0; j < W; ++j) {
-                            const int b = n_blk * BLOCK_N + keep0 + j;
-                            if (b < p.N) {
-                                const float other = __bfloat162float(xch[(keep0 + j) * 64 + fl]);
-                                const float gv = is_up ? other : bf16_round(mine[j]);
-                                const float uv = is_up ? bf16_round(mine[j]) : other;
-                                out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
-                            }
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // xch is free for the next tile
-                }
-            } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
-                // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
-                // partial[split][b][feature] fp32; lanes write consecutive features (coalesced).
-                float* out = reinterpret_cast<float*>(p.out);
-#pragma unroll 1
-                for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, v);
-                    tmem_ld_wait();
-                    if (row < p.M) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int b = n_blk * BLOCK_N + c * 32 + j;
-                            if (b < p.N) out[((long long)split * p.N + b) * p.ldo + row] = __uint_as_float(v[j]);
-                        }
-                    }
-                }
-            } else if constexpr (EPI == DOTS_EPI_BF16_T) {
-                // swap-AB, no split: out[b][feature] = bf16(acc + bias[feature]); lanes = consecutive features.
-                bf16* out = reinterpret_cast<bf16*>(p.out);
-                const float bias_v = (p.bias != nullptr && row < p.M) ? __bfloat162float(p.bias[row]) : 0.f;
-#pragma unroll 1
-                for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, v);
-                    tmem_ld_wait();
-                    if (row < p.M) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int b = n_blk * BLOCK_N + c * 32 + j;
-                            if (b < p.N) out[(long long)b * p.ldo + row] = __float2bfloat16_rn(__uint_as_float(v[j]) + bias_v);
-                        }
-                    }
-                }
-            } else {
-                // Two 32-column chunks per iteration: both TMEM loads and (for the residual epilogue) all eight 16-byte
-                // residual loads are issued before the first use, so one iteration pays one memory latency, not two.
-                static_assert(BLOCK_N % 64 == 0, "generic epilogue walks the tile in 64-column steps");
-                bf16* out = reinterpret_cast<bf16*>(p.out);
-                const bool row_ok = row < p.M;
-#pragma unroll 1
-                for (int c = eg * (BLOCK_N / 64); c < (eg + 1) * (BLOCK_N / 64); c += 2) {
-                    uint32_t v[2][32];
-                    tmem_ld_32x32b_x32(t_row + c * 32, v[0]);
-                    tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[1]);
-                    const int col0 = n_blk * BLOCK_N + c * 32;
-                    uint4 rres[2][4];
-                    if constexpr (EPI == DOTS_EPI_RESIDUAL) {
-                        const bf16* rsrc = p.res + (long long)row * p.ldr + col0;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                rres[h][q] = (row_ok && col0 + h * 32 + q * 8 + 8 <= p.N)
-                                                 ? *reinterpret_cast<const uint4*>(rsrc + h * 32 + q * 8) : make_uint4(0, 0, 0, 0);
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = col0 + h * 32;
-                        if (!(row_ok && col < p.N)) continue;
-                        float f[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[h][j]);
-                        if constexpr (EPI == DOTS_EPI_BIAS || EPI == DOTS_EPI_BIAS_GELU) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (col + q * 8 + 8 <= p.N) {
-                                    uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col + q * 8));
-                                    f[q * 8 + 0] += bf16_lo(b.x); f[q * 8 + 1] += bf16_hi(b.x);
-                                    f[q * 8 + 2] += bf16_lo(b.y); f[q * 8 + 3] += bf16_hi(b.y);
-                                    f[q * 8 + 4] += bf16_lo(b.z); f[q * 8 + 5] += bf16_hi(b.z);
-                                    f[q * 8 + 6] += bf16_lo(b.w); f[q * 8 + 7] += bf16_hi(b.w);
-                                }
-                            }
-                        }
-                        if constexpr (EPI == DOTS_EPI_BIAS_GELU) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(bf16_round(f[j]));
-                        }
-                        if constexpr (EPI == DOTS_EPI_RESIDUAL) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 r = rres[h][q];
-                                f[q * 8 + 0] = bf16_round(f[q * 8 + 0]) + bf16_lo(r.x);
-                                f[q * 8 + 1] = bf16_round(f[q * 8 + 1]) + bf16_hi(r.x);
-                                f[q * 8 + 2] = bf16_round(f[q * 8 + 2]) + bf16_lo(r.y);
-                                f[q * 8 + 3] = bf16_round(f[q * 8 + 3]) + bf16_hi(r.y);
-                                f[q * 8 + 4] = bf16_round(f[q * 8 + 4]) + bf16_lo(r.z);
-                                f[q * 8 + 5] = bf16_round(f[q * 8 + 5]) + bf16_hi(r.z);
-                                f[q * 8 + 6] = bf16_round(f[q * 8 + 6]) + bf16_lo(r.w);
-                                f[q * 8 + 7] = bf16_round(f[q * 8 + 7]) + bf16_hi(r.w);
-                            }
-                        }
-                        bf16* dst = out + (long long)row * p.ldo + col;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (col + q * 8 + 8 <= p.N) {
-                                uint4 o;
-                                o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                                o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                                o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                                o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                                *reinterpret_cast<uint4*>(dst + q * 8) = o;
-                            }
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_tile<BLOCK_N, EPI>(p, row, m_blk, n_blk, split, t_row, eg, wq, lane, xch);
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -414,6 +423,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tmem_dealloc(tmem_base, S::TMEM_COLS);
     }
 }
+
+extern int g_gemm_pair;
 
 template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
@@ -431,9 +442,163 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     return 0;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per cluster of two CTAs.  Each CTA stages its own 128 rows of A
+// and HALF of the B tile (128 of its 256 rows) per k-block; the pair's tensor cores read both halves, so per CTA the B
+// traffic into shared memory and out of it is halved (stage = 16 + 16 KB -> six stages), which is what keeps a
+// 128-wide-M kernel off the shared-memory roofline.  The leader CTA (cluster rank 0) issues the MMAs and owns the `full`
+// barriers (both CTAs' TMA bytes are credited to them) and the `tmem_empty` barriers (both CTAs' epilogue warps arrive);
+// `empty` and `tmem_full` are signalled in both CTAs by multicast commits.
+constexpr int G2_STAGES = 6;
+constexpr int G2_HALF_N = 128;
+constexpr int G2_BLOCK_N = 256;
+constexpr int G2_A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
+constexpr int G2_B_BYTES = G2_HALF_N * BLOCK_K * 2;        // 16 KB
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]   (leader's copy is the live one)
+    uint64_t* empty_bar = bars + G2_STAGES;          // [STAGES]   per CTA
+    uint64_t* tmem_full = bars + 2 * G2_STAGES;      // [2]        per CTA
+    uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [2]        (leader's copy is the live one)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int num_tiles = p.m_blocks * p.n_blocks;   // m_blocks counts 256-row tiles here
+
+    if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_a); prefetch_tensormap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < G2_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 4 * EPI_GROUPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_ptr, 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // the peer's barriers exist before anything remote touches them
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            pdl_wait();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += n_pairs) {
+                const int n_blk = t % p.n_blocks, m_pair = t / p.n_blocks;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);      // both CTAs' tiles
+                    tma_load_2d_2sm(smem_a + stage * G2_A_BYTES, &tmap_a, kb * BLOCK_K, m_pair * 256 + (int)rank * BLOCK_M, full_leader);
+                    tma_load_2d_2sm(smem_b + stage * G2_B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * G2_BLOCK_N + (int)rank * G2_HALF_N, full_leader);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const bool elected = elect_one();
+            constexpr uint32_t idesc = umma_idesc_bf16(256, G2_BLOCK_N);
+            const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem_a));
+            const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b));
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = pair; t < num_tiles; t += n_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * G2_BLOCK_N;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = da0 + (uint64_t)(stage * (G2_A_BYTES >> 4));
+                    const uint64_t db = db0 + (uint64_t)(stage * (G2_B_BYTES >> 4));
+                    const uint32_t first = (kb > 0) ? 1u : 0u;
+                    if (elected) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : first);
+                        umma_commit_2sm(&empty_bar[stage], 3);                                   // slot free in both CTAs
+                        if (kb + 1 == p.num_k_blocks) umma_commit_2sm(&tmem_full[acc], 3);       // accumulators ready in both CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs: each owns 128 rows of the 256-row tile) =====================
+        pdl_wait();
+        const int wq = warp & 3;
+        const int eg = (warp - 4) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = pair; t < num_tiles; t += n_pairs) {
+            const int n_blk = t % p.n_blocks, m_pair = t / p.n_blocks;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_pair * 256 + (int)rank * BLOCK_M + wq * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * G2_BLOCK_N;
+            gemm_epilogue_tile<G2_BLOCK_N, EPI>(p, row, 0, n_blk, 0, t_row, eg, wq, lane, nullptr);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));     // the leader's barrier counts both CTAs
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // nobody leaves while the peer may still signal or read this CTA
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    auto kern = gemm2_bf16_tcgen05_kernel<EPI>;
+    static bool configured = false;
+    if (!configured) {
+        DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+        configured = true;
+    }
+    const int tiles = p.m_blocks * p.n_blocks;
+    int pairs = num_sms() / 2;
+    if (tiles < pairs) pairs = tiles;
+    DOTS_CHECK_CUDA(launch_ex_cluster(kern, dim3(2 * pairs), dim3(GEMM_THREADS), (size_t)G2_SMEM, stream, true, 2u, ta, tb, p));
+    return 0;
+}
+
 }  // namespace dots
 
 using namespace dots;
+
+namespace dots { int g_gemm_pair = 1; }      // CTA-pair (cta_group::2) kernel for large prefill GEMMs (default on); dots_set_gemm_pair()
+
+extern "C" int dots_set_gemm_pair(int enable) {
+    dots::g_gemm_pair = enable ? 1 : 0;
+    return 0;
+}
 
 extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
                               int M, int N, int K, int epilogue, const void* bias, const void* residual,
@@ -457,6 +622,29 @@ extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta, tb;
     if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M)) return -4;
+
+    // CTA-pair kernel (256 x 256 tiles) for problems with at least two waves of such tiles
+    const bool pair_ok = g_gemm_pair && (N % 256 == 0) && ((long long)((M + 255) / 256) * (N / 256) >= num_sms());
+    if (pair_ok && epilogue != DOTS_EPI_F32_PARTIAL_T && epilogue != DOTS_EPI_BF16_T && epilogue != DOTS_EPI_SWIGLU_T) {
+        if ((epilogue == DOTS_EPI_BIAS || epilogue == DOTS_EPI_BIAS_GELU) && !bias) {
+            set_error("dots_gemm_bf16: bias epilogue without bias pointer");
+            return -1;
+        }
+        if (epilogue == DOTS_EPI_RESIDUAL) {
+            DOTS_REQUIRE(residual && ldr % 8 == 0, "dots_gemm_bf16: residual epilogue needs residual pointer, ldr %% 8 == 0");
+        }
+        p.m_blocks = (M + 255) / 256;
+        p.n_blocks = N / 256;
+        CUtensorMap tb2;
+        if (make_tmap_2d_bf16(&tb2, W, N, K, ldw, G2_HALF_N)) return -4;
+        switch (epilogue) {
+            case DOTS_EPI_STORE: return launch_gemm2<DOTS_EPI_STORE>(ta, tb2, p, st);
+            case DOTS_EPI_BIAS: return launch_gemm2<DOTS_EPI_BIAS>(ta, tb2, p, st);
+            case DOTS_EPI_BIAS_GELU: return launch_gemm2<DOTS_EPI_BIAS_GELU>(ta, tb2, p, st);
+            case DOTS_EPI_RESIDUAL: return launch_gemm2<DOTS_EPI_RESIDUAL>(ta, tb2, p, st);
+            case DOTS_EPI_SWIGLU: return launch_gemm2<DOTS_EPI_SWIGLU>(ta, tb2, p, st);
+        }
+    }
 
     if (epilogue == DOTS_EPI_SWIGLU) {
         DOTS_REQUIRE(N % 256 == 0, "dots_gemm_bf16: SWIGLU epilogue needs N %% 256 == 0 (got %d)", N);

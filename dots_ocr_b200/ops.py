@@ -320,6 +320,11 @@ def decode_chain(attn, w_o, w_gu, w_down, w_qkv_next, partial, resid, normed, ac
     _lib.check(rc, "dots_decode_chain")
 
 
+def set_gemm_pair(enable: bool) -> None:
+    """CTA-pair (cta_group::2) kernel for large prefill GEMMs."""
+    _lib.check(_lib.load().dots_set_gemm_pair(int(bool(enable))), "dots_set_gemm_pair")
+
+
 def set_pdl(enable: bool) -> None:
     """Programmatic dependent launch between consecutive kernels (default on)."""
     _lib.check(_lib.load().dots_set_pdl(int(bool(enable))), "dots_set_pdl")

@@ -48,6 +48,9 @@ DOTS_API int dots_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * setup and TMEM allocation of kernel N+1 overlap the tail of kernel N.  0 = plain stream order. */
 DOTS_API int dots_set_pdl(int enable);
 
+/* 1: large prefill GEMMs run on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles per 2-CTA cluster); 0: one CTA per tile. */
+DOTS_API int dots_set_gemm_pair(int enable);
+
 /* ---- dense contractions (tcgen05 / TMEM / TMA) -------------------------------------------- */
 
 /* out[M, N(/2)] = epilogue(A[M, K] * W[N, K]^T).  Replaces every nn.Linear / Conv2d-as-GEMM on the

@@ -443,3 +443,27 @@ def test_decode_chain_matches_per_op_kernels(B, H, I, QKV, so, sd, sq, gen):
         assert torch.equal(normed, normed2)
         if with_qkv:
             assert torch.equal(part[: sq * B * QKV], part2[: sq * B * QKV])
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(20000, 1536, 1536, "store"), (43808, 4608, 1536, "store"), (43808, 1536, 1536, "res"),
+                                        (26000, 2048, 1536, "bias"), (20000, 2048, 640, "gelu"), (43808, 8448, 1536, "swiglu"),
+                                        (33111, 1536, 4224, "res")])
+def test_gemm_cta_pair_matches_single_cta(M, N, K, epi, gen):
+    """cta_group::2 kernel (256 x 256 tiles on CTA pairs) vs the one-CTA kernel on the same inputs: same MMA k-order, so equal."""
+    ops = _ops()
+    a, w = _rand((M, K), gen), _rand((N, K), gen, 0.03)
+    bias = _rand((N,), gen) if epi in ("bias", "gelu") else None
+    res0 = _rand((M, N), gen) if epi == "res" else None
+    e = {"store": ops.EPI_STORE, "bias": ops.EPI_BIAS, "gelu": ops.EPI_BIAS_GELU, "res": ops.EPI_RESIDUAL, "swiglu": ops.EPI_SWIGLU}[epi]
+    outs = []
+    try:
+        for pair in (False, True):
+            ops.set_gemm_pair(pair)
+            out = torch.full((M, N // 2 if epi == "swiglu" else N), float("nan"), device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a, w, out=out, epilogue=e, bias=bias, residual=res0)
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        ops.set_gemm_pair(True)         # library default
+    assert not torch.isnan(outs[1].float()).any()
+    assert torch.equal(outs[0], outs[1]), float((outs[0].float() - outs[1].float()).abs().max())

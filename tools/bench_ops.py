@@ -59,10 +59,14 @@ def main():
                 r = rnd(M, N); f = lambda: ops.gemm(a, w, out=r, epilogue=ops.EPI_RESIDUAL, residual=r)
             else:
                 f = lambda: ops.gemm(a, w, epilogue=ops.EPI_SWIGLU)
+            ops.set_gemm_pair(False)
             ms = timeit(f)
+            ops.set_gemm_pair(True)
+            ms2 = timeit(f)
             tf = 2.0 * M * N * K / ms / 1e9
             ref = timeit(lambda: torch.matmul(a, w.t()))
-            print(json.dumps(dict(k="gemm", M=M, N=N, K=K, epi=epi, ms=round(ms, 4), tflops=round(tf, 1),
+            print(json.dumps(dict(k="gemm", M=M, N=N, K=K, epi=epi, ms=round(ms, 4), tflops=round(tf, 1), pair_ms=round(ms2, 4),
+                                  pair_tflops=round(2.0 * M * N * K / ms2 / 1e9, 1),
                                   cublas_ms=round(ref, 4), cublas_tflops=round(2.0 * M * N * K / ref / 1e9, 1))), flush=True)
             del a, w
     if "skinny" in only:
