@@ -133,13 +133,14 @@ def attn_varlen(q, k, v, out, cu_seqlens, max_seqlen: int, n_q_heads: int, n_kv_
     if PROFILE is not None:        # algorithmic FLOPs: 4 * L^2 * d per head (half that when causal)
         lens = (cu_seqlens[1:] - cu_seqlens[:-1]).double()
         work = float((lens * lens).sum().item()) * 4.0 * head_dim * n_q_heads * (0.5 if causal else 1.0)
-    if impl == "tc":
+    if impl in ("tc", "pair"):
+        fn = _lib.load().dots_attn_varlen_fwd_tc if impl == "tc" else _lib.load().dots_attn_varlen_fwd_pair
         with _Prof("attn_fwd_prefill" if causal else "attn_fwd_vit", work):
-            rc = _lib.load().dots_attn_varlen_fwd_tc(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),
+            rc = fn(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),
                                                      _p(out), _ll(out.stride(0)), _p(cu_seqlens), cu_seqlens.numel() - 1,
                                                      int(max_seqlen), _ll(q.shape[0]), n_q_heads, n_kv_heads, head_dim,
                                                      int(causal), C.c_float(scale), _stream())
-        _lib.check(rc, "dots_attn_varlen_fwd_tc")
+        _lib.check(rc, "dots_attn_varlen_fwd_" + impl)
         return out
     with _Prof("attn_fwd_prefill" if causal else "attn_fwd_vit", work):
         rc = _lib.load().dots_attn_varlen_fwd(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),

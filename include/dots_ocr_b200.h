@@ -92,6 +92,13 @@ DOTS_API int dots_attn_varlen_fwd_tc(const void* q, long long q_stride, const vo
                             int max_seqlen, long long total_tokens, int n_q_heads, int n_kv_heads, int head_dim,
                             int causal, float softmax_scale, void* stream);
 
+/* Same contract on CTA pairs (tcgen05 cta_group::2): a cluster of two CTAs covers 512 query rows and shares every K/V tile,
+ * each CTA staging half of it (halves the shared-memory traffic that bounds the single-CTA kernel). */
+DOTS_API int dots_attn_varlen_fwd_pair(const void* q, long long q_stride, const void* k, long long k_stride, const void* v,
+                              long long v_stride, void* out, long long o_stride, const int* cu_seqlens, int n_seqs,
+                              int max_seqlen, long long total_tokens, int n_q_heads, int n_kv_heads, int head_dim,
+                              int causal, float softmax_scale, void* stream);
+
 /* One-token-per-sequence attention over the KV cache [batch, n_kv_heads, ctx_max, 128]
  * (replaces DynamicCache + sdpa/flash decode, transformers/cache_utils.py:102-120, [Q]:227-241).
  * ctx_len[b] = number of visible keys (current token's key already appended).

@@ -25,7 +25,8 @@ def _ref_attn(q, k, v, causal, group):
     ([100, 37, 256], 2, 2, False, 1.0), ([1369], 12, 12, False, 1.0), ([5476], 2, 2, False, 1.0),
     ([5476], 1, 1, False, 6.0),            # peaked scores: exercises the lazy-rescale path
     ([70, 1, 300], 6, 1, True, 1.0), ([1625], 12, 2, True, 1.0), ([1625, 900], 6, 1, True, 5.0)])
-def test_attn_tc(lens, hq, hkv, causal, scale_q):
+@pytest.mark.parametrize("impl", ["tc", "pair"])
+def test_attn_tc(lens, hq, hkv, causal, scale_q, impl):
     from dots_ocr_b200 import ops
     g = torch.Generator(device=DEV).manual_seed(1)
     T = sum(lens)
@@ -36,7 +37,7 @@ def test_attn_tc(lens, hq, hkv, causal, scale_q):
     q, k, v = qkv[:, : hq * 128], qkv[:, hq * 128:(hq + hkv) * 128], qkv[:, (hq + hkv) * 128:]
     out = torch.full((T, hq * 128), float("nan"), device=DEV, dtype=torch.bfloat16)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
-    ops.attn_varlen(q, k, v, out, cu, max(lens), hq, hkv, causal, 128 ** -0.5, impl="tc")
+    ops.attn_varlen(q, k, v, out, cu, max(lens), hq, hkv, causal, 128 ** -0.5, impl=impl)
     torch.cuda.synchronize()
     assert not torch.isnan(out.float()).any(), "rows left unwritten / NaN"
     a = 0

@@ -5,7 +5,7 @@ name=$1; shift
 cd "$(dirname "$0")/.."
 out=dots_ocr_b200/build/variants; mkdir -p $out/$name
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
-for f in common gemm_tcgen05 attn_fwd_mma attn_fwd_tcgen05 attn_decode decode_chain elementwise; do
+for f in common gemm_tcgen05 attn_fwd_mma attn_fwd_tcgen05 attn_fwd_tcgen05_pair attn_decode decode_chain elementwise; do
   nvcc $FLAGS "$@" -c dots_ocr_b200/csrc/$f.cu -o $out/$name/$f.o &
 done
 wait
