@@ -33,12 +33,22 @@ constexpr int FA_BM = 128;          // rows per query tile (two tiles per CTA)
 constexpr int FA_BN = FA_BN_KEYS;   // keys per KV tile: 64 (S double-buffered in TMEM) or 128 (one S buffer per chain)
 constexpr int FA_SBUF = (FA_BN == 64) ? 2 : 1;      // S buffers per chain (TMEM: 2 x 64 or 1 x 128 columns)
 static_assert(FA_BN == 64 || FA_BN == 128, "FA_BN_KEYS must be 64 or 128");
-constexpr int FA_THREADS = 384;
+#ifndef FA_SPLIT_N
+#define FA_SPLIT_N 1
+#endif
+constexpr int FA_SPLIT = FA_SPLIT_N;    // softmax warps per TMEM lane quarter and chain: 2 = each thread handles half of a row's key columns
+static_assert(FA_SPLIT == 1 || (FA_SPLIT == 2 && FA_BN_KEYS == 128), "the split softmax is written for 128-key tiles");
+constexpr int FA_THREADS = 128 + 256 * FA_SPLIT;
 constexpr int FA_QTILE_BYTES = FA_BM * FA_D * 2;     // 32 KB = two [128 x 64] swizzle boxes
 constexpr int FA_KVTILE_BYTES = FA_BN * FA_D * 2;    // 16 KB = two [64 x 64] swizzle boxes
 constexpr int FA_KSTAGES = (FA_BN == 64) ? 4 : 3;
 constexpr int FA_VSTAGES = (FA_BN == 64) ? 4 : 2;
-constexpr int FA_SMEM = 2 * FA_QTILE_BYTES + (FA_KSTAGES + FA_VSTAGES) * FA_KVTILE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+// FA_SPLIT == 2 adds a 2 KB row-max / row-sum exchange buffer between the two column halves; with 128-key tiles that only fits the
+// 227 KB limit without alignment slack, so that build requires (and checks) a 1024-byte aligned dynamic shared memory base.
+constexpr int FA_SMEM = (FA_SPLIT_N == 2)
+    ? 2 * FA_QTILE_BYTES + (FA_KSTAGES + FA_VSTAGES) * FA_KVTILE_BYTES + 512 /*barriers*/ + 2048 /*exchange*/ + 512
+    : 2 * FA_QTILE_BYTES + (FA_KSTAGES + FA_VSTAGES) * FA_KVTILE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+static_assert(FA_SMEM <= 232448, "shared memory budget");
 
 struct FaParams {
     const int* cu;
@@ -126,6 +136,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     uint64_t* p_full = s_full + 4;              // [2][2]                 softmax -> MMA: P_t(j) written over buffer j&1
     uint64_t* pv_done = p_full + 4;             // [2][2]                 MMA -> softmax: O_t += P_t(j) V_j retired
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 4);
+    float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2 chains][2 halves][128 rows] (FA_SPLIT == 2)
+    if (FA_SPLIT == 2 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
 
     const int seq = blockIdx.z, head = blockIdx.y;
     const int tok0 = p.cu[seq];
@@ -145,7 +157,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mbar_init(q_full, 1);
         for (int i = 0; i < FA_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }   // released by both issuing warps
         for (int i = 0; i < FA_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], FA_SPLIT == 1 ? 128 : 8); mbar_init(&pv_done[i], 1); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -162,7 +174,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     constexpr uint32_t tmem_base = 0u;
 
     // register hand-over: 128 x (168 - dec) released >= 256 x (inc - 168) acquired
-    if (warp < 4) {
+    if (FA_SPLIT == 1 && warp < 4) {
         if (FA_BN == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     }
@@ -269,7 +281,146 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 if (more) commit(&k_empty[jn % FA_KSTAGES]);
             }
         }
-    } else if (warp >= 4) {
+    } else if (FA_SPLIT == 2 && warp >= 4) {
+#if FA_SPLIT_N == 2
+        // =============================== softmax, two warps per lane quarter: each thread owns HALF of a row's key columns ===============================
+        // Halving the per-thread work halves the S -> P latency of a chain (the kernel is bound by that hand-off chain, not by
+        // MUFU or issue slots); the two halves agree on the row max through shared memory, keep partial row sums and each
+        // finishes 64 of the 128 output dims.
+        const int t = (warp - 4) >> 3;                   // chain
+        const int hh = ((warp - 4) >> 2) & 1;            // column half
+        const int wq = warp & 3;                         // TMEM lane quarter
+        const int row = wq * 32 + lane;
+        const int qi = q0 + t * FA_BM + row;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + t * 256;
+        const uint32_t tSh = tS + hh * 64;               // my 64 score columns
+        const uint32_t tPh = tS + hh * 32;               // my 32 packed-P columns
+        const uint32_t tOh = tS + 128 + hh * 64;         // my 64 output dims
+        float m_run = -INFINITY;
+        float l_run = 0.f;                               // partial row sum over my columns
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(&s_full[t * 2], j & 1);
+            tc_fence_after();
+            const int k0 = j * FA_BN + hh * 64;
+            const bool need_mask = (k0 + 64 > L) || (CAUSAL && (k0 + 63 > q0 + t * FA_BM + wq * 32));
+            // ---- pass 1: row max of my half ----
+            float mxl = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float s[32];
+                tmem_ld_32x32b_x32(tSh + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld_wait();
+                if (need_mask) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int kj = k0 + c * 32 + i;
+                        if (kj >= L || (CAUSAL && kj > qi)) s[i] = -INFINITY;
+                    }
+                }
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) m4[q] = fmaxf(m4[q], fmaxf(s[i + 2 * q], s[i + 2 * q + 1]));
+                }
+                mxl = fmaxf(mxl, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            }
+            float* xb = xch + t * 256;      // single buffer: the second barrier of a step orders its reads before the next step's writes
+            xb[hh * 128 + row] = mxl;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+            const float mx = fmaxf(mxl, xb[(hh ^ 1) * 128 + row]);
+            // lazy rescale: both halves see the same (mx, m_run) and take the same decision
+            const bool need = (mx > m_run) && ((mx - m_run) * p.scale_log2 > 8.0f);
+            if (__any_sync(0xffffffffu, need)) {
+                const float m_new = need ? mx : m_run;
+                const float alpha = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_new) * p.scale_log2);
+                if (j > 0) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tOh + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x32b_x32(tOh + c * 32, v);
+                    }
+                }
+                l_run *= alpha;
+                m_run = m_new;
+            }
+            const float mneg = (m_run == -INFINITY) ? 0.f : -m_run * p.scale_log2;
+            const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), mn2 = pack_f32x2(mneg, mneg);
+            uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+            // ---- pass 2: p = exp2(s * scale - m * scale), bf16 P over my packed columns ----
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float s[32];
+                tmem_ld_32x32b_x32(tSh + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld_wait();
+                if (need_mask) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int kj = k0 + c * 32 + i;
+                        if (kj >= L || (CAUSAL && kj > qi)) s[i] = -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint64_t x2 = ffma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), sc2, mn2);
+                    float x0, x1;
+                    unpack_f32x2(x2, x0, x1);
+                    const float p0 = ex2f(x0), p1 = ex2f(x1);
+                    acc2[i & 3] = fadd_f32x2(acc2[i & 3], pack_f32x2(p0, p1));
+                    pk[c * 16 + i] = pack_bf16x2(p0, p1);
+                }
+            }
+            // every thread of the chain must have finished READING S before anyone overwrites it with P: my partner's columns
+            // [0, 32) of S are my partner's P target and vice versa
+            tc_fence_before();
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+            tc_fence_after();
+            tmem_st_32x32b_x32(tPh, pk);
+            {
+                float a0, a1, b0, b1;
+                unpack_f32x2(fadd_f32x2(acc2[0], acc2[1]), a0, a1);
+                unpack_f32x2(fadd_f32x2(acc2[2], acc2[3]), b0, b1);
+                l_run += (a0 + a1) + (b0 + b1);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t * 2]);
+        }
+        // ---- epilogue: combine the partial row sums, then my 64 dims of O_t / l -> bf16 -> global ----
+        float* xb = xch + t * 256;
+        xb[hh * 128 + row] = l_run;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        const float l_tot = l_run + xb[(hh ^ 1) * 128 + row];
+        mbar_wait(&pv_done[t * 2], (n_kv - 1) & 1);
+        tc_fence_after();
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        bf16* dst = p.o + (long long)(tok0 + qi) * p.os + head * FA_D + hh * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tOh + c * 32, v);
+            tmem_ld_wait();
+            if (qi < L) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv, __uint_as_float(v[q * 8 + 1]) * inv);
+                    o4.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv, __uint_as_float(v[q * 8 + 3]) * inv);
+                    o4.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv, __uint_as_float(v[q * 8 + 5]) * inv);
+                    o4.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv, __uint_as_float(v[q * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = o4;
+                }
+            }
+        }
+#endif
+    } else if (FA_SPLIT == 1 && warp >= 4) {
         // =============================== softmax warpgroups ===============================
         if (FA_BN == 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
