@@ -58,8 +58,10 @@ def test_full_size_single_page_matches_hf_bf16():
 
 
 def test_full_size_logits_random_weights():
-    """Pre-sampling logits at the real dimensions, N(0, 0.02) weights (no peaked head), teacher-forced on the oracle's ids:
-    max |engine - HF bf16| <= 0.06 sigma(logits), the tolerance stated in tests/test_engine_gpu.py."""
+    """Pre-sampling logits at the real dimensions, N(0, 0.02) weights (no peaked head), teacher-forced on the oracle's ids.
+    70 bf16 layers deep, two correct bf16 pipelines differ by more than the 0.06 sigma seen on the 2-layer config, so the
+    criterion is relative: the engine's error against the fp32 oracle (same weights, fp32 arithmetic on the GPU) must be no
+    worse than 1.5 x the error HF's own bf16 forward shows against it (floor 0.06 sigma)."""
     from dots_ocr_b200 import config, weights
     from dots_ocr_b200.engine import Engine
     from dots_ocr_b200.utils.image_utils import vit_grid, token_counts
@@ -77,17 +79,27 @@ def test_full_size_logits_random_weights():
     orc = DotsOracle(cfg, ck, torch.bfloat16, DEV)
     ref_ids = orc.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N).cpu()
     new = ref_ids[:, ids.shape[1]:]
-    ref_logits = orc.teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()            # [1, N, V] fp32 view of bf16 logits
+    ref16 = orc.teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()               # [1, N, V]
     del orc
+    torch.cuda.empty_cache()
+    orc32 = DotsOracle(cfg, ck, torch.float32, DEV)
+    ref32 = orc32.teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()
+    del orc32
     torch.cuda.empty_cache()
     eng = Engine(cfg, ck, DEV)
     out = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N, forced_ids=new, return_logits=True)
     got = out.logits.float().cpu()
-    sd = float(ref_logits.std())
-    err = float((got - ref_logits).abs().max()) / sd
-    print(f"full-size logits: max |engine - HF bf16| = {err:.4f} sigma")
-    assert got.shape == ref_logits.shape == (1, N, cfg.text.vocab_size)
-    assert err < 6e-2, err
+    sd = float(ref32.std())
+    err_eng = float((got - ref32).abs().max()) / sd
+    err_hf = float((ref16 - ref32).abs().max()) / sd
+    err_pair = float((got - ref16).abs().max()) / sd
+    print(f"full-size logits (sigma units): engine-vs-fp32 {err_eng:.4f}  HF-bf16-vs-fp32 {err_hf:.4f}  engine-vs-HF-bf16 {err_pair:.4f}")
+    assert got.shape == ref32.shape == (1, N, cfg.text.vocab_size)
+    assert err_eng < max(1.5 * err_hf, 6e-2), (err_eng, err_hf)
+    # wherever the fp32 oracle's top-1 margin clears twice the observed bf16 error, the engine's argmax agrees
+    top2 = ref32.topk(2, -1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 2 * max(err_eng, err_hf) * sd
+    assert torch.equal(got.argmax(-1)[clear], ref32.argmax(-1)[clear])
 
 
 def test_attention_tc_long_sequence_cross_check():
