@@ -48,6 +48,35 @@ __global__ void cast_pad_kernel(const void* __restrict__ in, int in_is_bf16, lon
     }
 }
 
+// uint8 RGB page [H, W, 3] (already smart-resized, H and W multiples of patch * merge) -> normalised, patchified bf16 rows
+// [gh * gw, ldo]: row order = 2x2 merge blocks contiguous, row layout (c, py, px), columns >= 3 * patch^2 zero.
+// Same arithmetic as the host processor + cast: bf16( (float(u8) - 255 * mean_c) / (255 * std_c) )   (fp32, IEEE divide)
+// (transformers/models/qwen2_vl/image_processing_qwen2_vl.py:148-232).
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int patch, int merge, float m0, float m1, float m2,
+                                   float s0, float s1, float s2, bf16* __restrict__ out, int ldo) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int gh = H / patch, gw = W / patch;
+    const int pd = 3 * patch * patch;
+    const long long total = (long long)gh * gw * ldo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / ldo), col = (int)(i % ldo);
+        float v = 0.f;
+        if (col < pd) {
+            // r = ((bh * (gw / merge) + bw) * merge + ih) * merge + iw
+            const int iw = r % merge, ih = (r / merge) % merge;
+            const int blk = r / (merge * merge);
+            const int bw = blk % (gw / merge), bh = blk / (gw / merge);
+            const int c = col / (patch * patch), py = (col / patch) % patch, px = col % patch;
+            const int y = (bh * merge + ih) * patch + py, x = (bw * merge + iw) * patch + px;
+            const float u = (float)img[((long long)y * W + x) * 3 + c];
+            const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+            v = __fdiv_rn(__fsub_rn(u, m), sd);
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
 // ------------------------------------------------------------------ RMSNorm (one warp per row)
 // out = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )        (Qwen2RMSNorm, modeling_qwen2.py:258-263)
 constexpr int NORM_MAX_CHUNKS = 8;     // per lane; cols <= 8 * 32 * 8 = 2048 on the register path
@@ -571,6 +600,19 @@ extern "C" int dots_cast_pad_bf16(const void* in, int in_is_bf16, long long rows
     const long long total = rows * (ldo / 2);
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
     DOTS_CHECK_CUDA(launch_ex(cast_pad_kernel, dim3(blocks), dim3(256), (size_t)(0), ST(stream), true, in, in_is_bf16, rows, cols, (bf16*)out, ldo));
+    return 0;
+}
+
+extern "C" int dots_patchify_u8(const void* img_hwc, int H, int W, int patch, int merge, const float* mean255, const float* std255,
+                                void* out, int ldo, void* stream) {
+    DOTS_REQUIRE(img_hwc && out && mean255 && std255, "dots_patchify_u8: null pointer");
+    DOTS_REQUIRE(patch > 0 && merge > 0 && H > 0 && W > 0 && H % (patch * merge) == 0 && W % (patch * merge) == 0,
+                 "dots_patchify_u8: H, W must be multiples of patch * merge (got %d x %d)", H, W);
+    DOTS_REQUIRE(ldo >= 3 * patch * patch && ldo % 8 == 0, "dots_patchify_u8: ldo must cover 3 * patch^2 and keep 16-byte rows");
+    const long long total = (long long)(H / patch) * (W / patch) * ldo;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    DOTS_CHECK_CUDA(launch_ex(patchify_u8_kernel, dim3(blocks), dim3(256), (size_t)(0), ST(stream), true, (const uint8_t*)img_hwc, H, W, patch, merge,
+                              mean255[0], mean255[1], mean255[2], std255[0], std255[1], std255[2], (bf16*)out, ldo));
     return 0;
 }
 

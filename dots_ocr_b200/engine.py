@@ -115,7 +115,27 @@ class Engine:
 
     # ------------------------------------------------------------------------------ vision
     @torch.no_grad()
-    def encode_images(self, pixel_values: torch.Tensor, image_grid_thw, return_layers: bool = False):
+    def encode_pages_u8(self, pages, return_layers: bool = False):
+        """ViT forward from uint8 RGB pages already on the device (each [H, W, 3], smart-resized: H, W multiples of 28).
+        The rescale / normalise / patchify half of the HF image processor runs on the GPU (dots_patchify_u8, SURVEY.md
+        section 8f N1), so a page costs 3 B per pixel of host->device traffic instead of 12."""
+        from .processing import CLIP_MEAN, CLIP_STD
+        v = self.cfg.vision
+        mean255 = (torch.tensor(CLIP_MEAN, dtype=torch.float32) * 255.0).tolist()
+        std255 = (torch.tensor(CLIP_STD, dtype=torch.float32) * 255.0).tolist()
+        grid = [[1, int(pg.shape[0]) // v.patch_size, int(pg.shape[1]) // v.patch_size] for pg in pages]
+        S = sum(g[1] * g[2] for g in grid)
+        xin = torch.empty((S, self.patch_k), device=self.device, dtype=torch.bfloat16)
+        a = 0
+        for pg, g in zip(pages, grid):
+            n = g[1] * g[2]
+            ops.patchify_u8(pg.to(self.device).contiguous(), v.patch_size, v.spatial_merge_size, mean255, std255, self.patch_k, out=xin[a:a + n])
+            a += n
+        self.launches += len(grid)
+        return self.encode_images(None, grid, return_layers=return_layers, _xin=xin)
+
+    @torch.no_grad()
+    def encode_images(self, pixel_values: Optional[torch.Tensor], image_grid_thw, return_layers: bool = False, _xin: Optional[torch.Tensor] = None):
         """DotsVisionTransformer.forward ([V] dots_ocr.py:580-611): pixel_values [sum S, 588] ->
         image embeddings [sum S / 4, hidden]."""
         v = self.cfg.vision
@@ -127,8 +147,11 @@ class Engine:
                 seqlens.append(int(h) * int(w))
                 ghw.append([int(h), int(w)])
         S = sum(seqlens)
-        pv = pixel_values.to(dev)
-        assert pv.shape == (S, v.patch_dim), (pv.shape, S, v.patch_dim)
+        if _xin is None:
+            pv = pixel_values.to(dev)
+            assert pv.shape == (S, v.patch_dim), (pv.shape, S, v.patch_dim)
+        else:
+            assert _xin.shape == (S, self.patch_k) and _xin.dtype == torch.bfloat16
         cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0).tolist()), dtype=torch.int32, device=dev)
         ghw_t = torch.tensor(ghw, dtype=torch.int32, device=dev)
         max_seqlen = max(seqlens)
@@ -136,7 +159,7 @@ class Engine:
         scale = v.head_dim ** -0.5
 
         cos, sin = ops.vit_rope_table(cu, ghw_t, self.v_inv_freq, v.spatial_merge_size, S)
-        xin = ops.cast_pad(pv.contiguous(), self.patch_k)
+        xin = _xin if _xin is not None else ops.cast_pad(pv.contiguous(), self.patch_k)
         x = ops.gemm(xin, self.v_patch_w, epilogue=ops.EPI_BIAS, bias=self.v_patch_b)
         del xin
         x = ops.rmsnorm(x, self.v_patch_norm, v.rms_norm_eps, out=x)
@@ -308,7 +331,7 @@ class Engine:
                  pixel_values: Optional[torch.Tensor] = None, image_grid_thw=None, max_new_tokens: int = 16,
                  eos_token_id: Optional[int] = None, pad_token_id: int = 0, forced_ids: Optional[torch.Tensor] = None,
                  return_logits: bool = False, use_graph: bool = True, image_embeds: Optional[torch.Tensor] = None,
-                 **unused) -> GenerateOutput:
+                 pages_u8=None, **unused) -> GenerateOutput:
         """HF-shaped greedy generation: returns ids [B, T + N'] including the prompt (parser.py:110-113)."""
         t = self.cfg.text
         dev = self.device
@@ -330,7 +353,9 @@ class Engine:
         cu = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         cu[1:] = lens.cumsum(0).to(torch.int32)
 
-        if image_embeds is None and pixel_values is not None:
+        if image_embeds is None and pages_u8 is not None:
+            image_embeds = self.encode_pages_u8(pages_u8)          # GPU half of the image processor (uint8 pages in)
+        elif image_embeds is None and pixel_values is not None:
             image_embeds = self.encode_images(pixel_values, image_grid_thw)
         slots = None
         if image_embeds is not None:

@@ -194,6 +194,21 @@ def cast_pad(x: torch.Tensor, ldo: int, out: Optional[torch.Tensor] = None) -> t
     return out
 
 
+def patchify_u8(img: torch.Tensor, patch: int, merge: int, mean255, std255, ldo: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 HWC page on the device -> normalised, patchified, zero-padded bf16 rows [gh * gw, ldo] (merge-block token order)."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
+    H, W = int(img.shape[0]), int(img.shape[1])
+    rows = (H // patch) * (W // patch)
+    if out is None:
+        out = torch.empty((rows, ldo), device=img.device, dtype=torch.bfloat16)
+    assert out.shape == (rows, ldo) and out.is_contiguous()
+    m = (C.c_float * 3)(*[float(v) for v in mean255])
+    sd = (C.c_float * 3)(*[float(v) for v in std255])
+    rc = _lib.load().dots_patchify_u8(_p(img), H, W, patch, merge, m, sd, _p(out), ldo, _stream())
+    _lib.check(rc, "dots_patchify_u8")
+    return out
+
+
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _bf16_2d(x, "x")
     if out is None:

@@ -61,6 +61,25 @@ def preprocess_image(image, min_pixels: Optional[int] = None, max_pixels: Option
     return x.contiguous(), torch.tensor([[1, gh, gw]], dtype=torch.int64)
 
 
+def preprocess_image_u8(image, min_pixels: Optional[int] = None, max_pixels: Optional[int] = None, patch: int = 14,
+                        merge: int = 2) -> torch.Tensor:
+    """Host half of the GPU pre-processing path: PIL image -> smart-resized uint8 HWC tensor (the bicubic + antialias resize stays
+    on the CPU so that it is the same torchvision resize the stock processor runs); rescale / normalise / patchify happen in
+    dots_patchify_u8 on the device."""
+    import torchvision.transforms.v2.functional as tvF
+    from torchvision.transforms import InterpolationMode
+    if not isinstance(image, (np.ndarray, torch.Tensor)):
+        image = np.asarray(to_rgb(image))
+    img = torch.from_numpy(np.array(image, copy=True))
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3, "expect uint8 HWC RGB"
+    H, W = img.shape[:2]
+    rh, rw = smart_resize(H, W, factor=patch * merge, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
+    if (rh, rw) != (H, W):
+        chw = tvF.resize(img.permute(2, 0, 1).contiguous(), [rh, rw], interpolation=InterpolationMode.BICUBIC, antialias=True)
+        img = chw.permute(1, 2, 0)
+    return img.contiguous()
+
+
 class SyntheticTokenizer:
     """Byte-level stand-in (ids 0..255 = bytes) with the three image specials mapped onto the config's
     reserved ids.  NOT the dots.ocr tokenizer: decoded text is meaningless with synthetic weights."""
@@ -84,6 +103,18 @@ class SyntheticTokenizer:
 
     def decode(self, ids: Sequence[int]) -> str:
         return bytes(int(i) for i in ids if 0 <= int(i) < 256).decode("utf-8", errors="replace")
+
+
+def build_text_inputs(tokenizer: SyntheticTokenizer, n_image_tokens: Sequence[int], prompts: Sequence[str]):
+    """Left-padded input_ids + attention_mask for prompts whose images contribute `n_image_tokens[i]` <|imgpad|> slots."""
+    rows = [tokenizer.encode_chat(prompt, n) for prompt, n in zip(prompts, n_image_tokens)]
+    T = max(len(r) for r in rows)
+    ids = torch.full((len(rows), T), tokenizer.pad_token_id, dtype=torch.int64)
+    mask = torch.zeros((len(rows), T), dtype=torch.int64)
+    for i, r in enumerate(rows):
+        ids[i, T - len(r):] = torch.tensor(r)
+        mask[i, T - len(r):] = 1
+    return dict(input_ids=ids, attention_mask=mask)
 
 
 def build_inputs(tokenizer: SyntheticTokenizer, images: Sequence, prompts: Sequence[str], min_pixels=None, max_pixels=None,

@@ -122,6 +122,13 @@ DOTS_API int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, co
 /* pixel_values [rows, cols] fp32 (or bf16) -> bf16 [rows, ldo] zero-padded ([V]:586 `.to(dtype)`). */
 DOTS_API int dots_cast_pad_bf16(const void* in, int in_is_bf16, long long rows, int cols, void* out, int ldo, void* stream);
 
+/* GPU half of the image processor: uint8 RGB page [H, W, 3] (already smart-resized; H, W multiples of patch * merge) ->
+ * rescale + normalise + patchify -> bf16 rows [H/patch * W/patch, ldo] in 2x2-merge token order, zero-padded to ldo.
+ * mean255 / std255 are HOST pointers to 3 floats each (255 * CLIP mean / std).  Bit-identical to the host fp32 processor
+ * followed by dots_cast_pad_bf16 ([C] image_processing_qwen2_vl.py:148-232). */
+DOTS_API int dots_patchify_u8(const void* img_hwc, int H, int W, int patch, int merge, const float* mean255, const float* std255,
+                     void* out, int ldo, void* stream);
+
 /* RMSNorm, fp32 statistics: out = bf16(bf16(x * rsqrt(mean x^2 + eps)) * w)   ([Q]:258-263, [V]:450,456,518). */
 DOTS_API int dots_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, long long rows, int cols,
                  float eps, void* stream);

@@ -251,3 +251,25 @@ def test_argument_validation_happens_before_any_cuda_call():
     rc = lib.dots_rmsnorm(None, ctypes.c_longlong(8), None, None, ctypes.c_longlong(8), ctypes.c_longlong(4), 4100,
                           ctypes.c_float(1e-6), None)
     assert rc == -1
+
+
+def test_u8_preprocessing_host_half_matches_full_processor():
+    """preprocess_image_u8 (resize only) + the normalise/patchify arithmetic == preprocess_image (what dots_patchify_u8 does on the GPU)."""
+    from dots_ocr_b200.processing import preprocess_image, preprocess_image_u8, build_text_inputs, SyntheticTokenizer, CLIP_MEAN, CLIP_STD
+    from dots_ocr_b200 import config
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (100, 150, 3), generator=g, dtype=torch.uint8).numpy()     # not a multiple of 28: exercises the resize
+    pv, grid = preprocess_image(img)
+    u8 = preprocess_image_u8(img)
+    gh, gw = int(grid[0, 1]), int(grid[0, 2])
+    assert u8.shape == (gh * 14, gw * 14, 3) and u8.dtype == torch.uint8
+    x = u8.permute(2, 0, 1).float()
+    mean = torch.tensor(CLIP_MEAN, dtype=torch.float32) * 255.0
+    std = torch.tensor(CLIP_STD, dtype=torch.float32) * 255.0
+    x = (x - mean[:, None, None]) / std[:, None, None]
+    x = x.view(3, gh // 2, 2, 14, gw // 2, 2, 14).permute(1, 4, 2, 5, 0, 3, 6).reshape(gh * gw, 588)
+    assert torch.equal(x, pv)
+    tok = SyntheticTokenizer(config.tiny())
+    t = build_text_inputs(tok, [gh * gw // 4, 3], ["ab", "c"])
+    assert t["input_ids"].shape == t["attention_mask"].shape and int(t["attention_mask"][0].sum()) == gh * gw // 4 + 6 + 2
+    assert int((t["input_ids"][0] == tok.image_token_id).sum()) == gh * gw // 4

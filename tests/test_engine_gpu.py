@@ -186,3 +186,28 @@ def test_decode_chain_kernel_on_off_identical(tiny):
     finally:
         eng.decode_chain = False
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_gpu_preprocessing_path_matches_host(tiny):
+    """uint8 pages normalised / patchified on the GPU (Engine.generate(pages_u8=...)) == host processor output fed as pixel_values."""
+    from dots_ocr_b200.processing import preprocess_image
+    cfg, d = tiny
+    ck, eng = d["peaked"]
+    g = torch.Generator().manual_seed(21)
+    imgs = [torch.randint(0, 256, (112, 168, 3), generator=g, dtype=torch.uint8), torch.randint(0, 256, (224, 112, 3), generator=g, dtype=torch.uint8)]
+    pvs, grids, rows = [], [], []
+    for im in imgs:
+        pv, gr = preprocess_image(im.numpy(), min_pixels=im.shape[0] * im.shape[1], max_pixels=im.shape[0] * im.shape[1])
+        pvs.append(pv); grids.append(gr)
+        rows.append(torch.cat([torch.randint(0, 2000, (4,), generator=g), torch.full((pv.shape[0] // 4,), cfg.image_token_id),
+                               torch.randint(0, 2000, (3,), generator=g)]))
+    T = max(r.numel() for r in rows)
+    ids = torch.zeros((2, T), dtype=torch.long)
+    mask = torch.zeros((2, T), dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, T - r.numel():] = r
+        mask[i, T - r.numel():] = 1
+    a = eng.generate(ids, attention_mask=mask, pixel_values=torch.cat(pvs).to(DEV), image_grid_thw=torch.cat(grids), max_new_tokens=10)
+    b = eng.generate(ids, attention_mask=mask, pages_u8=[im.to(DEV) for im in imgs], max_new_tokens=10)
+    assert torch.equal(a.image_embeds, b.image_embeds)
+    assert torch.equal(a.sequences, b.sequences)

@@ -467,3 +467,20 @@ def test_gemm_cta_pair_matches_single_cta(M, N, K, epi, gen):
         ops.set_gemm_pair(True)         # library default
     assert not torch.isnan(outs[1].float()).any()
     assert torch.equal(outs[0], outs[1]), float((outs[0].float() - outs[1].float()).abs().max())
+
+
+@pytest.mark.parametrize("H,W", [(56, 84), (1036, 1036), (280, 1008)])
+def test_patchify_u8_matches_host_processor(H, W):
+    """GPU rescale + normalise + patchify == host fp32 processor followed by cast_pad, bit for bit."""
+    from dots_ocr_b200.processing import preprocess_image, CLIP_MEAN, CLIP_STD
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+    pv, grid = preprocess_image(img.numpy(), min_pixels=H * W, max_pixels=H * W)       # no resize: sizes are multiples of 28
+    assert grid.tolist() == [[1, H // 14, W // 14]]
+    ref = ops.cast_pad(pv.to(DEV), 640)
+    mean255 = (torch.tensor(CLIP_MEAN, dtype=torch.float32) * 255.0).tolist()
+    std255 = (torch.tensor(CLIP_STD, dtype=torch.float32) * 255.0).tolist()
+    got = ops.patchify_u8(img.to(DEV), 14, 2, mean255, std255, 640)
+    assert got.shape == ref.shape
+    assert torch.equal(got, ref)
