@@ -271,5 +271,5 @@ def test_u8_preprocessing_host_half_matches_full_processor():
     assert torch.equal(x, pv)
     tok = SyntheticTokenizer(config.tiny())
     t = build_text_inputs(tok, [gh * gw // 4, 3], ["ab", "c"])
-    assert t["input_ids"].shape == t["attention_mask"].shape and int(t["attention_mask"][0].sum()) == gh * gw // 4 + 6 + 2
+    assert t["input_ids"].shape == t["attention_mask"].shape and int(t["attention_mask"][0].sum()) == gh * gw // 4 + 5 + len("ab")
     assert int((t["input_ids"][0] == tok.image_token_id).sum()) == gh * gw // 4
