@@ -388,10 +388,9 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
     p.n_q_heads = n_q_heads; p.n_kv_heads = n_kv_heads; p.group = n_q_heads / n_kv_heads; p.n_splits = n_splits;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
-        configured = true;
     }
     // K / V cache layer slice [batch * n_kv_heads * ctx_max, 128] bf16, fetched as [64 keys][64 dims] 128-B-swizzled boxes
     const unsigned long long rows = (unsigned long long)batch * n_kv_heads * (unsigned long long)p.ctx_max;

@@ -224,11 +224,10 @@ extern "C" int dots_attn_varlen_fwd(const void* q, long long q_stride, const voi
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid((max_seqlen + ATT_BM - 1) / ATT_BM, n_q_heads, n_seqs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        configured = true;
     }
     if (causal) attn_fwd_mma_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(p);
     else attn_fwd_mma_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(p);

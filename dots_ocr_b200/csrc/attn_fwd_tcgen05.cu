@@ -577,11 +577,10 @@ extern "C" int dots_attn_varlen_fwd_tc(const void* q, long long q_stride, const 
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid((max_seqlen + 2 * FA_BM - 1) / (2 * FA_BM), n_q_heads, n_seqs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        configured = true;
     }
     if (causal) attn_fwd_tcgen05_kernel<true><<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, p);
     else attn_fwd_tcgen05_kernel<false><<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, p);

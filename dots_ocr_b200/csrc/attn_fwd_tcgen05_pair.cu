@@ -14,6 +14,9 @@
 // Barriers: q/k/v `full` live in the leader (TMA of both CTAs completes on them); k/v `empty`, `s_full`, `pv_done` exist in
 // both CTAs and are signalled by multicast commits; `p_full` lives in the leader and collects one arrival per softmax warp
 // of both CTAs.  SURVEY.md §8a rows a10, a19.
+//
+// STATUS: experiment.  Passes the parity tests, but measures 650 vs 1080 TFLOP/s for the single-CTA kernel: attention is bound
+// by the per-chain hand-off latency, which cluster-scope barriers lengthen, not by shared-memory bandwidth.
 #include "common.h"
 #include "ptx.cuh"
 #include "../../include/dots_ocr_b200.h"
@@ -349,11 +352,10 @@ extern "C" int dots_attn_varlen_fwd_pair(const void* q, long long q_stride, cons
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid(2 * ((max_seqlen + 4 * F2_BM - 1) / (4 * F2_BM)), n_q_heads, n_seqs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-        configured = true;
     }
     if (causal) DOTS_CHECK_CUDA(launch_ex_cluster(attn_fwd_tcgen05_pair_kernel<true>, grid, dim3(F2_THREADS), (size_t)F2_SMEM, st, false, 2u, tq, tk, tv, p));
     else DOTS_CHECK_CUDA(launch_ex_cluster(attn_fwd_tcgen05_pair_kernel<false>, grid, dim3(F2_THREADS), (size_t)F2_SMEM, st, false, 2u, tq, tk, tv, p));

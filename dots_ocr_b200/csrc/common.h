@@ -13,6 +13,9 @@ typedef __nv_bfloat16 bf16;
 // Error plumbing: every C-ABI entry returns 0 or a negative code; text via dots_last_error().
 void set_error(const char* fmt, ...);
 int num_sms();
+// Per-device one-time setup (cudaFuncSetAttribute is per device): true the first time it is called on the current device
+// with this flag array.
+bool first_use_on_device(bool (&flags)[64]);
 
 #define DOTS_CHECK_CUDA(expr)                                                              \
     do {                                                                                   \

@@ -458,11 +458,10 @@ extern "C" int dots_decode_chain(const void* attn, const void* w_o, const void* 
         maps.a[3] = maps.a[0]; maps.b[3] = maps.b[0];
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(decode_chain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem<32>::TOTAL));
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(decode_chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem<64>::TOTAL));
-        configured = true;
     }
     // Every CTA must be resident at once (device-wide phase barriers): one per SM.  Programmatic dependent launch lets the
     // CTAs start streaming weights while the attention kernel before them drains; all mutable state is read after pdl_wait().

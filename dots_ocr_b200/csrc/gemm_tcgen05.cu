@@ -430,10 +430,9 @@ template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
     using S = GemmSmem<BLOCK_N, EPI>;
     auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        configured = true;
     }
     const int tiles = p.m_blocks * p.n_blocks * p.splits;
     const int slots = num_sms() * S::MIN_CTAS;
@@ -577,10 +576,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 template <int EPI>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
     auto kern = gemm2_bf16_tcgen05_kernel<EPI>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-        configured = true;
     }
     const int tiles = p.m_blocks * p.n_blocks;
     int pairs = num_sms() / 2;

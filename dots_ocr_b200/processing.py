@@ -3,8 +3,8 @@
 Restates the stock ``Qwen2VLImageProcessor`` (fast/torchvision variant the reference selects with
 ``use_fast=True``, ``dots_ocr/parser.py:75``) for the dots.ocr settings: patch 14, merge 2,
 temporal_patch_size 1, CLIP mean/std, bicubic + antialias resize on the uint8 tensor
-(``transformers/models/qwen2_vl/image_processing_qwen2_vl.py:148-232``).  ``tests/test_processing.py``
-checks bit-equality with the transformers class on the reference's demo images.
+(``transformers/models/qwen2_vl/image_processing_qwen2_vl.py:148-232``).
+``tests/test_cpu_host.py::test_preprocess_image_equals_hf_processor`` checks bit-equality with the transformers class.
 
 The chat template and tokenizer live in the HF checkpoint directory, which does not exist offline;
 ``SyntheticTokenizer`` is a byte-level stand-in used only to exercise the plumbing.
