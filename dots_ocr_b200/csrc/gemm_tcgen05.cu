@@ -104,52 +104,55 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int row,
         // swap-AB decode GEMM over the gate|up weight: tile rows 0-63 are gate features, rows 64-127 the matching up
         // features (warps 0,1 / 2,3 of this group).  Up warps publish bf16(up) through shared memory, gate warps
         // finish  act[b][f] = bf16( bf16(silu(bf16 g)) * bf16 u )  -- the same rounding points as the prefill epilogue.
-        // (epilogue group 0 only: the exchange below is a 4-warp named barrier)
-        if (eg == 0) {
-        // All four warps share the SiLU work: gate warps publish bf16(g) of the upper half of the batch tile, up warps
-        // publish bf16(u) of the lower half; then gate warps finish batch columns [0, BN/2) and up warps [BN/2, BN).
-        bf16* out = reinterpret_cast<bf16*>(p.out);
-        const int fl = (wq & 1) * 32 + lane;                 // feature within the 64-block
-        const bool is_up = wq >= 2;
-        constexpr int HALF = BLOCK_N / 2;
-        static_assert(HALF % 16 == 0, "batch tile halves are read in 16-column TMEM chunks");
-        const int f = m_blk * 64 + fl;
+        // Each epilogue group (4 warps, one per TMEM lane quarter) owns half of the batch columns when the tile is wide enough;
+        // inside a group all four warps share the SiLU work: gate warps publish bf16(g) of the upper half of the group's columns,
+        // up warps publish bf16(u) of the lower half; then gate warps finish the lower half and up warps the upper half.
+        constexpr int GROUPS = (BLOCK_N >= 64) ? EPI_GROUPS : 1;       // 16-column TMEM chunks: a group needs >= 32 columns
+        if (eg < GROUPS) {
+            bf16* out = reinterpret_cast<bf16*>(p.out);
+            const int fl = (wq & 1) * 32 + lane;                 // feature within the 64-block
+            const bool is_up = wq >= 2;
+            constexpr int SPAN = BLOCK_N / GROUPS;               // batch columns of this group
+            constexpr int HALF = SPAN / 2;
+            static_assert(HALF % 16 == 0, "batch tile halves are read in 16-column TMEM chunks");
+            const int g0 = eg * SPAN;
+            const int f = m_blk * 64 + fl;
 #pragma unroll 1
-        for (int h0 = 0; h0 < HALF; h0 += 32) {              // 32 batch columns of each half per pass (register budget)
-            constexpr int W = HALF < 32 ? HALF : 32;
-            float mine[W];
-            const int pub0 = (is_up ? 0 : HALF) + h0, keep0 = (is_up ? HALF : 0) + h0;
+            for (int h0 = 0; h0 < HALF; h0 += 32) {              // 32 batch columns of each half per pass (register budget)
+                constexpr int W = HALF < 32 ? HALF : 32;
+                float mine[W];
+                const int pub0 = g0 + (is_up ? 0 : HALF) + h0, keep0 = g0 + (is_up ? HALF : 0) + h0;
 #pragma unroll
-            for (int c = 0; c < W / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_row + pub0 + c * 16, v);
-                tmem_ld_wait();
+                for (int c = 0; c < W / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_row + pub0 + c * 16, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) xch[(pub0 + c * 16 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
-            }
+                    for (int j = 0; j < 16; ++j) xch[(pub0 + c * 16 + j) * 64 + fl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                }
 #pragma unroll
-            for (int c = 0; c < W / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_row + keep0 + c * 16, v);
-                tmem_ld_wait();
+                for (int c = 0; c < W / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_row + keep0 + c * 16, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mine[c * 16 + j] = __uint_as_float(v[j]);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-            if (f < p.M / 2) {
+                    for (int j = 0; j < 16; ++j) mine[c * 16 + j] = __uint_as_float(v[j]);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");      // the four warps of this group only
+                if (f < p.M / 2) {
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    const int b = n_blk * BLOCK_N + keep0 + j;
-                    if (b < p.N) {
-                        const float other = __bfloat162float(xch[(keep0 + j) * 64 + fl]);
-                        const float gv = is_up ? other : bf16_round(mine[j]);
-                        const float uv = is_up ? bf16_round(mine[j]) : other;
-                        out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
+                    for (int j = 0; j < W; ++j) {
+                        const int b = n_blk * BLOCK_N + keep0 + j;
+                        if (b < p.N) {
+                            const float other = __bfloat162float(xch[(keep0 + j) * 64 + fl]);
+                            const float gv = is_up ? other : bf16_round(mine[j]);
+                            const float uv = is_up ? bf16_round(mine[j]) : other;
+                            out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
+                        }
                     }
                 }
             }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // xch is free for the next tile
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");      // xch rows of this group are free for the next tile
         }
     } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
         // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
