@@ -48,6 +48,11 @@ def _page_tokens(cfg):
     return token_counts(*PAGE_HW, patch=cfg.vision.patch_size, merge=cfg.vision.spatial_merge_size)
 
 
+def _prompt_len():
+    from dots_ocr_b200.utils.image_utils import token_counts
+    return token_counts(*PAGE_HW)[1] + TEXT_TOKENS
+
+
 def _prompt_ids(cfg, batch, t_img, seed=7):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -223,10 +228,10 @@ def run_reference(args):
 
 
 def _config(args, world):
-    return {"workload": f"batch={args.batch} synthetic {PAGE_HW[0]}x{PAGE_HW[1]} pages per GPU, ViT encode + prefill(T=1625) + "
+    return {"workload": f"batch={args.batch} synthetic {PAGE_HW[0]}x{PAGE_HW[1]} pages per GPU, ViT encode + prefill(T={_prompt_len()}) + "
                         f"greedy decode N={args.new_tokens} (BASELINE configs[2]; x{world} GPUs = configs[3] sharding)",
             "pages_per_gpu": args.batch, "global_pages": args.batch * world, "new_tokens": args.new_tokens,
-            "prompt_tokens": 1369 + TEXT_TOKENS, "parallelism": f"dp{world} (page shards, model replicated, no collective)",
+            "prompt_tokens": _prompt_len(), "parallelism": f"dp{world} (page shards, model replicated, no collective)",
             "l2": "inputs larger than L2 (pixel_values 824 MB fp32 per step; weights 6.1 GB streamed every decode step)",
             "weights": "synthetic N(0,0.02) seed 0, real architecture (ViT 1.26B + LLM 1.78B)"}
 
@@ -390,6 +395,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--new-tokens", dest="new_tokens", type=int, default=512)
     ap.add_argument("--preset", default="full")
+    ap.add_argument("--page", type=int, default=1024, help="synthetic page edge in pixels (1024 = the headline workload; 1960 with "
+                    "--batch 4 --new-tokens 2048 = BASELINE configs[4], the long-context case)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--gemm-pair", dest="gemm_pair", type=int, default=None, choices=[0, 1],
@@ -397,6 +404,8 @@ def main():
     ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
     ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "pair", "mma"])
     args = ap.parse_args()
+    global PAGE_HW
+    PAGE_HW = (args.page, args.page)
     if args.impl == "reference":
         run_reference(args)
     else:
