@@ -1,12 +1,13 @@
 """``DotsOCRParser`` with the reference's constructor and public methods
 (``dots_ocr/parser.py:22-36, 255-322``), its model call served by the B200 engine.
 
-Only the hot-path seam is re-implemented here: ``_load_hf_model`` / ``_inference_with_hf`` /
-``_inference_with_vllm`` / ``get_prompt`` / ``parse_image`` / ``parse_file``.  The CPU
-post-processing of the decoded text (layout JSON repair, markdown, drawing)
-and PDF rasterisation (row 9, needs PyMuPDF) are out of scope for this tier: results are saved
-as the raw response plus, when it parses, the JSON.  See INTEGRATION.md for patching the
-reference's own parser instead.
+The hot-path seam is re-implemented here (``_load_hf_model`` / ``_inference_with_hf`` / ``_inference_with_vllm`` /
+``get_prompt`` / ``parse_image`` / ``parse_file``) together with the post-decode CPU pipeline of
+``_parse_single_image`` (``parser.py:143-253``): the decoded layout JSON is mapped back to page coordinates and
+rendered to Markdown by ``utils/layout_utils.py`` / ``utils/format_transformer.py``, whose behaviour is pinned against
+the reference functions (``tests/test_postprocess.py``).  Not reproduced: drawing the layout on the page (PyMuPDF), the
+``OutputCleaner`` JSON repair, and PDF rasterisation (PyMuPDF).  See INTEGRATION.md for patching the reference's own
+parser instead.
 """
 from __future__ import annotations
 
@@ -87,31 +88,66 @@ class DotsOCRParser:
         return prompt
 
     # -- pages --------------------------------------------------------------------------------
+    def _fetch_image(self, origin_image, min_pixels, max_pixels):
+        """RGB conversion + the resize ``fetch_image`` applies when a pixel budget is given (image_utils.py:116-138)."""
+        from .processing import to_rgb
+        image = to_rgb(origin_image)
+        if min_pixels or max_pixels:
+            rh, rw = smart_resize(image.height, image.width, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
+            image = image.resize((rw, rh))
+        return image
+
     def _parse_single_image(self, origin_image, prompt_mode, save_dir, save_name, source="image", page_idx=0, bbox=None):
+        """One page: prompt -> model -> layout cells in page coordinates (.json) + Markdown (.md, _nohf.md), as the reference
+        writes them (parser.py:143-253).  The page image is saved undecorated as <name>.jpg (no PyMuPDF drawing)."""
+        from .utils.layout_utils import post_process_output
+        from .utils.format_transformer import layoutjson2md
         min_pixels, max_pixels = self.min_pixels, self.max_pixels
         if prompt_mode == "prompt_grounding_ocr":
             min_pixels = min_pixels or MIN_PIXELS
             max_pixels = max_pixels or MAX_PIXELS
-        from .processing import to_rgb
-        image = to_rgb(origin_image)
+        if min_pixels is not None:
+            assert min_pixels >= MIN_PIXELS, f"min_pixels should >= {MIN_PIXELS}"
+        if max_pixels is not None:
+            assert max_pixels <= MAX_PIXELS, f"max_pixels should <= {MAX_PIXELS}"
+        image = self._fetch_image(origin_image, min_pixels, max_pixels)
+        input_height, input_width = smart_resize(image.height, image.width)
         prompt = self.get_prompt(prompt_mode, bbox, origin_image, image, min_pixels=min_pixels, max_pixels=max_pixels)
         response = self._inference_with_hf(image, prompt) if self.use_hf else self._inference_with_vllm(image, prompt)
-        result = {'page_no': page_idx, 'input_height': image.height, 'input_width': image.width}
+        result = {'page_no': page_idx, 'input_height': input_height, 'input_width': input_width}
         if source == 'pdf':
             save_name = f"{save_name}_page_{page_idx}"
         os.makedirs(save_dir, exist_ok=True)
-        try:
-            cells = json.loads(response)
-            path = os.path.join(save_dir, f"{save_name}.json")
+
+        def write(path, text):
             with open(path, 'w', encoding='utf-8') as w:
-                json.dump(cells, w, ensure_ascii=False)
-            result['layout_info_path'] = path
-        except (TypeError, ValueError):
-            result['filtered'] = True
+                w.write(text if text is not None else "")
+
+        image_path = os.path.join(save_dir, f"{save_name}.jpg")
+        origin_rgb = origin_image if getattr(origin_image, "mode", "RGB") == "RGB" else origin_image.convert("RGB")
+        origin_rgb.save(image_path)
+        result['layout_image_path'] = image_path
         md_path = os.path.join(save_dir, f"{save_name}.md")
-        with open(md_path, 'w', encoding='utf-8') as w:
-            w.write(response if response is not None else "")
-        result['md_content_path'] = md_path
+        if prompt_mode in ('prompt_layout_all_en', 'prompt_layout_only_en', 'prompt_grounding_ocr'):
+            cells, filtered = post_process_output(response, prompt_mode, origin_image, image, min_pixels=min_pixels, max_pixels=max_pixels)
+            json_path = os.path.join(save_dir, f"{save_name}.json")
+            result['layout_info_path'] = json_path
+            if filtered and prompt_mode != 'prompt_layout_only_en':
+                with open(json_path, 'w', encoding='utf-8') as w:
+                    json.dump(response, w, ensure_ascii=False)
+                write(md_path, cells)
+                result.update({'md_content_path': md_path, 'filtered': True})
+            else:
+                with open(json_path, 'w', encoding='utf-8') as w:
+                    json.dump(cells, w, ensure_ascii=False)
+                if prompt_mode != 'prompt_layout_only_en' and not filtered:
+                    nohf_path = os.path.join(save_dir, f"{save_name}_nohf.md")
+                    write(md_path, layoutjson2md(origin_rgb, cells, text_key='text'))
+                    write(nohf_path, layoutjson2md(origin_rgb, cells, text_key='text', no_page_hf=True))
+                    result.update({'md_content_path': md_path, 'md_content_nohf_path': nohf_path})
+        else:
+            write(md_path, response)
+            result['md_content_path'] = md_path
         return result
 
     def parse_image(self, input_path, filename, prompt_mode, save_dir, bbox=None):

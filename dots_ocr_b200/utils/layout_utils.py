@@ -1,0 +1,69 @@
+"""Post-decode layout handling: map the model's bounding boxes between the original page and the
+smart-resized image the model saw, and interpret the decoded response.
+
+Mirrors the call surface of ``dots_ocr/utils/layout_utils.py`` (``pre_process_bboxes`` :115-144, ``post_process_cells``
+:146-193, ``is_legal_bbox`` :195-200, ``post_process_output`` :202-228); behaviour is pinned against the reference functions
+executed in the build container (``tests/golden/postprocess.json``).  The reference's ``OutputCleaner`` (JSON repair of
+malformed responses, 622 lines) is not reproduced: a response that does not parse is returned as text with ``filtered=True``.
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from .consts import MIN_PIXELS, MAX_PIXELS
+from .image_utils import smart_resize
+
+TEXT_ONLY_MODES = ("prompt_ocr", "prompt_table_html", "prompt_table_latex", "prompt_formula_latex")
+
+
+def _model_size(input_width: int, input_height: int, min_pixels: Optional[int], max_pixels: Optional[int]) -> Tuple[int, int]:
+    """(width, height) of the image the model really saw: the server side applies smart_resize once more."""
+    h, w = smart_resize(input_height, input_width, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
+    return w, h
+
+
+def _rescale(bbox: Sequence, sx: float, sy: float) -> List[int]:
+    # the reference divides by the scale and truncates towards zero, coordinate by coordinate
+    return [int(float(bbox[0]) / sx), int(float(bbox[1]) / sy), int(float(bbox[2]) / sx), int(float(bbox[3]) / sy)]
+
+
+def pre_process_bboxes(origin_image, bboxes: List[List], input_width: int, input_height: int, factor: int = 28,
+                       min_pixels: int = 3136, max_pixels: int = 11289600) -> List[List[int]]:
+    """Original-page boxes -> coordinates in the image the model sees (grounding prompts)."""
+    assert isinstance(bboxes, list) and len(bboxes) > 0 and isinstance(bboxes[0], list)
+    ow, oh = origin_image.size
+    mw, mh = _model_size(input_width, input_height, min_pixels, max_pixels)
+    return [_rescale(b, ow / mw, oh / mh) for b in bboxes]
+
+
+def post_process_cells(origin_image, cells: List[Dict], input_width: int, input_height: int, factor: int = 28,
+                       min_pixels: int = 3136, max_pixels: int = 11289600) -> List[Dict]:
+    """Model-space boxes of the decoded layout cells -> original-page coordinates (other keys are kept)."""
+    assert isinstance(cells, list) and len(cells) > 0 and isinstance(cells[0], dict)
+    ow, oh = origin_image.size
+    mw, mh = _model_size(input_width, input_height, min_pixels, max_pixels)
+    sx, sy = mw / ow, mh / oh
+    out = []
+    for cell in cells:
+        c = dict(cell)
+        c["bbox"] = _rescale(cell["bbox"], sx, sy)
+        out.append(c)
+    return out
+
+
+def is_legal_bbox(cells: List[Dict]) -> bool:
+    return all(c["bbox"][2] > c["bbox"][0] and c["bbox"][3] > c["bbox"][1] for c in cells)
+
+
+def post_process_output(response, prompt_mode: str, origin_image, input_image, min_pixels=None, max_pixels=None):
+    """Decoded text -> (cells in page coordinates, filtered=False), or (text, True) when the layout JSON does not parse.
+    Text-only prompt modes return the response unchanged (as the reference does)."""
+    if prompt_mode in TEXT_ONLY_MODES:
+        return response
+    try:
+        cells = post_process_cells(origin_image, json.loads(response), input_image.width, input_image.height,
+                                   min_pixels=min_pixels, max_pixels=max_pixels)
+        return cells, False
+    except Exception:
+        return response, True

@@ -222,8 +222,18 @@ def test_parser_plumbing_with_a_fake_runner(tmp_path):
     img = tmp_path / "page.png"
     Image.new("RGBA", (120, 90), (255, 0, 0, 128)).save(img)
     res = p.parse_file(str(img), prompt_mode="prompt_layout_only_en")
-    assert res[0]["page_no"] == 0 and os.path.exists(res[0]["layout_info_path"]) and os.path.exists(res[0]["md_content_path"])
+    assert res[0]["page_no"] == 0 and os.path.exists(res[0]["layout_info_path"]) and os.path.exists(res[0]["layout_image_path"])
+    assert "md_content_path" not in res[0]                         # detection only: no Markdown (parser.py:219)
+    assert (res[0]["input_height"], res[0]["input_width"]) == (84, 112)
     assert fake.seen[0] == (120, 90) and "layout" in fake.seen[1]
+    res = p.parse_file(str(img), prompt_mode="prompt_layout_all_en")
+    import json as _json
+    cells = _json.load(open(res[0]["layout_info_path"]))
+    assert cells == [{"bbox": [1, 2, 3, 4], "category": "Text", "text": "x"}]          # 112/120 and 84/90 scales truncate back to the same ints
+    assert open(res[0]["md_content_path"]).read() == "x" and open(res[0]["md_content_nohf_path"]).read() == "x"
+    fake.infer = lambda image, prompt, max_new_tokens=0: "not json"
+    res = p.parse_file(str(img), prompt_mode="prompt_layout_all_en")
+    assert res[0].get("filtered") is True and open(res[0]["md_content_path"]).read() == "not json"
     with pytest.raises(ValueError):
         p.parse_file(str(tmp_path / "x.tiff"))
 
