@@ -1,0 +1,89 @@
+"""Request batching behind the one-page call surface.
+
+The reference fans pages out from up to ``num_thread`` (default 64) worker threads, each calling
+``inference_with_vllm(image, prompt, ...)`` for ONE page (``dots_ocr/parser.py:282-290``); the vLLM server batches them.  In process
+the same threads would serialise on the engine lock, one page per ``generate``.  ``BatchingRunner`` gives them the server's
+behaviour: callers block on a future while a single worker thread drains the queue into batches of up to ``max_batch`` pages
+(it waits at most ``max_wait_ms`` for stragglers once the first request of a batch has arrived) and runs one
+``PageRunner.infer_batch`` per batch, so concurrent callers share the ViT / prefill / decode launches.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from concurrent.futures import Future
+from typing import List, Optional
+
+
+class BatchingRunner:
+    def __init__(self, runner, max_batch: int = 64, max_wait_ms: float = 20.0):
+        self.runner = runner                      # anything with infer_batch(images, prompts, max_new_tokens) -> List[str]
+        self.engine = getattr(runner, "engine", None)
+        self.tokenizer = getattr(runner, "tokenizer", None)
+        self.max_batch = int(max_batch)
+        self.max_wait = float(max_wait_ms) / 1e3
+        import inspect
+        try:
+            self._takes_budgets = "budgets" in inspect.signature(runner.infer_batch).parameters      # per-caller token budgets
+        except (TypeError, ValueError):
+            self._takes_budgets = False
+        self._q: "queue.Queue" = queue.Queue()
+        self._closed = False
+        self.batches: List[int] = []              # sizes of the batches run so far (observability / tests)
+        self._worker = threading.Thread(target=self._loop, name="dots-b200-batcher", daemon=True)
+        self._worker.start()
+
+    # -- caller side ------------------------------------------------------------------------------------------------
+    def submit(self, image, prompt: str, max_new_tokens: int = 512) -> Future:
+        if self._closed:
+            raise RuntimeError("BatchingRunner is closed")
+        fut: Future = Future()
+        self._q.put((image, prompt, int(max_new_tokens), fut))
+        return fut
+
+    def infer(self, image, prompt: str, max_new_tokens: int = 512) -> str:
+        return self.submit(image, prompt, max_new_tokens).result()
+
+    def infer_batch(self, images, prompts, max_new_tokens: int = 512) -> List[str]:
+        futs = [self.submit(im, pr, max_new_tokens) for im, pr in zip(images, prompts)]
+        return [f.result() for f in futs]
+
+    def close(self, timeout: Optional[float] = 5.0) -> None:
+        self._closed = True
+        self._q.put(None)
+        self._worker.join(timeout)
+
+    # -- worker -----------------------------------------------------------------------------------------------------
+    def _loop(self) -> None:
+        while True:
+            first = self._q.get()
+            if first is None:
+                return
+            batch = [first]
+            stop = False
+            while len(batch) < self.max_batch:
+                try:
+                    item = self._q.get(timeout=self.max_wait)
+                except queue.Empty:
+                    break
+                if item is None:
+                    stop = True
+                    break
+                batch.append(item)
+            self._run(batch)
+            if stop:
+                return
+
+    def _run(self, batch) -> None:
+        # one generate for the whole batch at the largest token budget; every caller gets its own budget back
+        n_new = max(b[2] for b in batch)
+        self.batches.append(len(batch))
+        try:
+            kw = {"budgets": [b[2] for b in batch]} if self._takes_budgets else {}
+            texts = self.runner.infer_batch([b[0] for b in batch], [b[1] for b in batch], max_new_tokens=n_new, **kw)
+        except BaseException as e:          # noqa: BLE001 -- the error belongs to the callers, not to the worker thread
+            for b in batch:
+                b[3].set_exception(e)
+            return
+        for b, text in zip(batch, texts):
+            b[3].set_result(text)

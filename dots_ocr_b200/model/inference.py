@@ -23,10 +23,13 @@ def set_default_runner(runner) -> None:
 
 
 def get_default_runner():
+    """Process-wide runner: the engine behind a request batcher, so that the parser's thread fan-out (one page per call,
+    parser.py:282-290) shares generate() calls the way requests share a vLLM server's batches."""
     with _lock:
         if _state["runner"] is None:
+            from ..batching import BatchingRunner
             from ..runner import PageRunner
-            _state["runner"] = PageRunner.from_default()
+            _state["runner"] = BatchingRunner(PageRunner.from_default())
         return _state["runner"]
 
 

@@ -39,7 +39,8 @@ class PageRunner:
             ckpt = _weights.make_synthetic_checkpoint(cfg, 0, "peaked", device=device)
         return cls(Engine(cfg, ckpt, device), SyntheticTokenizer(cfg))
 
-    def infer_batch(self, images: Sequence, prompts: Sequence[str], max_new_tokens: int = 512, gpu_preprocess: bool = True) -> List[str]:
+    def infer_batch(self, images: Sequence, prompts: Sequence[str], max_new_tokens: int = 512, gpu_preprocess: bool = True,
+                    budgets: Optional[Sequence[int]] = None) -> List[str]:
         """gpu_preprocess: resize on the host (uint8), rescale / normalise / patchify on the GPU (3 B per pixel over PCIe instead of
         12); False = the reference's host processor output (fp32 pixel_values) as `generate` input."""
         n_new = max(1, min(int(max_new_tokens), self.cap))
@@ -58,7 +59,9 @@ class PageRunner:
                                        pad_token_id=self.tokenizer.pad_token_id, **kw)
             seq = out.sequences.cpu()
         T = inputs["input_ids"].shape[1]
-        return [self.tokenizer.decode(row[T:].tolist()) for row in seq]          # trim the prompt (parser.py:111-113)
+        # trim the prompt (parser.py:111-113); a batched caller may carry a smaller token budget than the batch ran with
+        lim = [n_new] * len(seq) if budgets is None else [max(1, min(int(b), n_new)) for b in budgets]
+        return [self.tokenizer.decode(row[T:T + k].tolist()) for row, k in zip(seq, lim)]
 
     def infer(self, image, prompt: str, max_new_tokens: int = 512) -> str:
         return self.infer_batch([image], [prompt], max_new_tokens)[0]

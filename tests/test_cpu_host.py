@@ -283,3 +283,44 @@ def test_u8_preprocessing_host_half_matches_full_processor():
     t = build_text_inputs(tok, [gh * gw // 4, 3], ["ab", "c"])
     assert t["input_ids"].shape == t["attention_mask"].shape and int(t["attention_mask"][0].sum()) == gh * gw // 4 + 5 + len("ab")
     assert int((t["input_ids"][0] == tok.image_token_id).sum()) == gh * gw // 4
+
+
+def test_batching_runner_groups_concurrent_callers():
+    """64 threads, one page each (the reference parser's fan-out) -> a few batched infer_batch calls, every caller gets ITS result."""
+    import threading
+    import time
+    from dots_ocr_b200.batching import BatchingRunner
+
+    class FakeRunner:
+        def __init__(self):
+            self.calls = []
+
+        def infer_batch(self, images, prompts, max_new_tokens=512):
+            self.calls.append((len(images), max_new_tokens))
+            time.sleep(0.05)                                   # a "generate" during which more requests queue up
+            return [f"{im}|{pr}|{max_new_tokens}" for im, pr in zip(images, prompts)]
+
+    fake = FakeRunner()
+    br = BatchingRunner(fake, max_batch=16, max_wait_ms=30)
+    out = {}
+
+    def work(i):
+        out[i] = br.infer(f"img{i}", f"p{i}", max_new_tokens=8 + (i % 3))
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(64)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(20)
+    br.close()
+    assert len(out) == 64 and all(out[i].startswith(f"img{i}|p{i}|") for i in range(64))
+    assert sum(n for n, _ in fake.calls) == 64 and max(n for n, _ in fake.calls) <= 16
+    assert len(fake.calls) <= 12, fake.calls                   # batched, not 64 single-page calls
+    assert all(m == 10 for n, m in fake.calls if n >= 3)       # a batch runs at its largest token budget
+
+    class Boom:
+        def infer_batch(self, images, prompts, max_new_tokens=512):
+            raise ValueError("engine failed")
+    br2 = BatchingRunner(Boom(), max_batch=4, max_wait_ms=5)
+    with pytest.raises(ValueError):
+        br2.infer("a", "b")
+    br2.close()

@@ -211,3 +211,33 @@ def test_gpu_preprocessing_path_matches_host(tiny):
     b = eng.generate(ids, attention_mask=mask, pages_u8=[im.to(DEV) for im in imgs], max_new_tokens=10)
     assert torch.equal(a.image_embeds, b.image_embeds)
     assert torch.equal(a.sequences, b.sequences)
+
+
+def test_batching_runner_matches_single_page_calls(tiny):
+    """The reference parser's fan-out (threads, one page per call) through BatchingRunner == the same pages one by one."""
+    import threading
+    from PIL import Image
+    from dots_ocr_b200.batching import BatchingRunner
+    from dots_ocr_b200.processing import SyntheticTokenizer
+    from dots_ocr_b200.runner import PageRunner
+    cfg, d = tiny
+    ck, eng = d["peaked"]
+    runner = PageRunner(eng, SyntheticTokenizer(cfg))
+    g = torch.Generator().manual_seed(77)
+    sizes = [(112, 168), (224, 112), (140, 140), (56, 280), (168, 168), (112, 112)]
+    pages = [Image.fromarray(torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8).numpy()) for h, w in sizes]
+    prompts = [f"prompt {i} " + "x" * i for i in range(len(pages))]
+    single = [runner.infer(pg, pr, max_new_tokens=12) for pg, pr in zip(pages, prompts)]
+    br = BatchingRunner(runner, max_batch=8, max_wait_ms=200)
+    out = [None] * len(pages)
+
+    def work(i):
+        out[i] = br.infer(pages[i], prompts[i], max_new_tokens=12)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(pages))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    br.close()
+    assert out == single
+    assert sum(br.batches) == len(pages) and len(br.batches) < len(pages)          # at least some calls shared a generate
