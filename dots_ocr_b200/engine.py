@@ -15,7 +15,6 @@ Layout in HBM (all bf16 unless noted):
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import List, Optional
+from typing import Optional  # noqa: F401
 
 from .model.inference import inference_with_vllm
 from .utils.consts import MIN_PIXELS, MAX_PIXELS, image_extensions

@@ -11,7 +11,6 @@ import os
 import threading
 from typing import List, Optional, Sequence
 
-import torch
 
 from . import config as _config
 from . import weights as _weights
