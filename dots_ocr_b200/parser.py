@@ -5,8 +5,8 @@ The hot-path seam is re-implemented here (``_load_hf_model`` / ``_inference_with
 ``get_prompt`` / ``parse_image`` / ``parse_file``) together with the post-decode CPU pipeline of
 ``_parse_single_image`` (``parser.py:143-253``): the decoded layout JSON is mapped back to page coordinates and
 rendered to Markdown by ``utils/layout_utils.py`` / ``utils/format_transformer.py``, whose behaviour is pinned against
-the reference functions (``tests/test_postprocess.py``).  Not reproduced: drawing the layout on the page (PyMuPDF), the
-``OutputCleaner`` JSON repair, and PDF rasterisation (PyMuPDF).  See INTEGRATION.md for patching the reference's own
+the reference functions, JSON repair of cut-off responses included (``tests/test_postprocess.py``).  Not reproduced: drawing
+the layout on the page and PDF rasterisation (both PyMuPDF).  See INTEGRATION.md for patching the reference's own
 parser instead.
 """
 from __future__ import annotations

@@ -3,8 +3,8 @@ smart-resized image the model saw, and interpret the decoded response.
 
 Mirrors the call surface of ``dots_ocr/utils/layout_utils.py`` (``pre_process_bboxes`` :115-144, ``post_process_cells``
 :146-193, ``is_legal_bbox`` :195-200, ``post_process_output`` :202-228); behaviour is pinned against the reference functions
-executed in the build container (``tests/golden/postprocess.json``).  The reference's ``OutputCleaner`` (JSON repair of
-malformed responses, 622 lines) is not reproduced: a response that does not parse is returned as text with ``filtered=True``.
+executed in the build container (``tests/golden/postprocess.json``).  A response that does not parse goes through
+``output_cleaner.OutputCleaner`` (the reference's JSON repair) and comes back as text with ``filtered=True``.
 """
 from __future__ import annotations
 
@@ -57,13 +57,19 @@ def is_legal_bbox(cells: List[Dict]) -> bool:
 
 
 def post_process_output(response, prompt_mode: str, origin_image, input_image, min_pixels=None, max_pixels=None):
-    """Decoded text -> (cells in page coordinates, filtered=False), or (text, True) when the layout JSON does not parse.
+    """Decoded text -> (cells in page coordinates, filtered=False), or (repaired text, True) when the layout JSON does not parse.
     Text-only prompt modes return the response unchanged (as the reference does)."""
     if prompt_mode in TEXT_ONLY_MODES:
         return response
+    cells = response
     try:
-        cells = post_process_cells(origin_image, json.loads(response), input_image.width, input_image.height,
-                                   min_pixels=min_pixels, max_pixels=max_pixels)
-        return cells, False
-    except Exception:
-        return response, True
+        cells = json.loads(cells)
+        return post_process_cells(origin_image, cells, input_image.width, input_image.height,
+                                  min_pixels=min_pixels, max_pixels=max_pixels), False
+    except Exception:       # noqa: BLE001 -- not JSON, not a list of cells, or a cell without a usable bbox
+        pass
+    from .output_cleaner import OutputCleaner
+    repaired = OutputCleaner().clean_model_output(cells)
+    if isinstance(repaired, list):
+        repaired = "\n\n".join(cell["text"] for cell in repaired if "text" in cell)
+    return repaired, True

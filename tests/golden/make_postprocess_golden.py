@@ -57,6 +57,64 @@ for mode, resp in [("prompt_layout_all_en", good), ("prompt_ocr", "raw text"), (
     r = L.post_process_output(resp, mode, page, seen)
     out["output"].append({"mode": mode, "response": resp, "out": list(r) if isinstance(r, tuple) else r, "tuple": isinstance(r, tuple)})
 
+# ---- OutputCleaner (dots_ocr/utils/output_cleaner.py:32-435) and the failure path of post_process_output -------------------
+import contextlib
+import io
+from dots_ocr.utils.output_cleaner import OutputCleaner   # noqa: E402
+
+def cell(i, cat="Text", text=None, bbox=None):
+    d = {"bbox": bbox or [i, i + 1, i + 10, i + 20], "category": cat}
+    if text is not None:
+        d["text"] = text
+    return d
+
+full = json.dumps([cell(i, text=f"line {i}") for i in range(6)])
+cases = [
+    full,
+    full[:-1],                                            # array never closed
+    full[: len(full) - 25],                               # cut inside the last cell
+    full[: full.find('"text"') + 12],                     # cut inside the first cell's text
+    '[{"bbox": [1, 2, 3, 4], "category": "Title", "text": "only one and it is cut',
+    '[{"bbox": [1, 2, 3], "category": "Title", "text": "three coords" ',
+    '[{"bbox": [1, 2, x, 4], "category": "Title", "text": "bad int',
+    '{"bbox": [1, 2, 3, 4], "category": "Text", "text": "a"}{"bbox": [5, 6, 7, 8], "category": "Text", "text": "b"}',
+    '[{"bbox": [1, 2, 3, 4], "category": "Text", "text": "a"} {"bbox": [5, 6, 7, 8], "category": "Text", "text": "b"}]',
+    json.dumps([cell(1, text="same")] * 4 + [cell(9, text="other")]),
+    json.dumps([cell(i, text="spam") for i in range(7)] + [cell(50, text="tail")]),
+    json.dumps([cell(i, text="spam") for i in range(4)]),
+    json.dumps([cell(3, text="a"), cell(3, text="b"), cell(4, text="c")]),
+    "not json at all",
+    "",
+    "[]",
+    '{"bbox": [1, 2, 3, 4], "category": "Text"}',
+    '[{"bbox": [1,2,3,4], "category": "Table", "text": "<table><tr><td>{x}</td></tr></table>"}, {"bbox": [5,6,7,8], "category": "Text", "text": "y"}]',
+    '[{"bbox": [1,2,3,4], "category": "Formula", "text": "a_{i}"}, {"bbox": [5,6,7,8], "category": "Text", "text": "z"',
+    "[" + ", ".join(json.dumps(cell(i, text="w" * 400)) for i in range(140)),            # > 50 000 chars, not closed
+    "[" + ", ".join(json.dumps(cell(i, text="w" * 400)) for i in range(140)) + "]",      # > 50 000 chars, closed: still loses its last cell
+    '[{"category": "Text", "text": "no bbox"}, {"bbox": [1,2,3,4], "category": "Text", "text": "ok"}]',
+    "42", "null", '"a string"',
+]
+list_cases = [
+    [cell(1, text="a"), {"bbox": [1, 2, 3], "category": "Text", "text": "three"}, {"bbox": [1, 2, 3]}, {"bbox": "oops", "category": "X"},
+     {"category": "Picture"}, {"text": "orphan"}, "junk", 7, cell(1, text="dup bbox")],
+    [],
+    [cell(i, text="spam") for i in range(6)],
+    [{"bbox": [[1, 2], 3, 4, 5], "category": "Text", "text": "nested"}, {"bbox": [[1, 2], 3, 4, 5], "category": "Text", "text": "nested2"}],
+    [cell(1)],
+]
+out["cleaner"] = []
+for c in cases + list_cases:
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = OutputCleaner().clean_model_output(c)
+    out["cleaner"].append({"in": c, "out": r})
+
+out["output_fail"] = []
+for resp in [cases[2], cases[3], cases[4], "not json", "[]", json.dumps([{"category": "Text", "text": "no bbox here"}]), json.dumps({"bbox": [1, 2, 3, 4]}),
+             cases[10], json.dumps([cell(1, text="a"), {"bbox": [1, 2, 3], "category": "Text", "text": "three"}])]:
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = L.post_process_output(resp, "prompt_layout_all_en", page, seen)
+    out["output_fail"].append({"response": resp, "out": list(r)})
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "postprocess.json")
 json.dump(out, open(path, "w"))
 print({k: len(v) for k, v in out.items()}, "->", path)

@@ -231,9 +231,9 @@ def test_parser_plumbing_with_a_fake_runner(tmp_path):
     cells = _json.load(open(res[0]["layout_info_path"]))
     assert cells == [{"bbox": [1, 2, 3, 4], "category": "Text", "text": "x"}]          # 112/120 and 84/90 scales truncate back to the same ints
     assert open(res[0]["md_content_path"]).read() == "x" and open(res[0]["md_content_nohf_path"]).read() == "x"
-    fake.infer = lambda image, prompt, max_new_tokens=0: "not json"
+    fake.infer = lambda image, prompt, max_new_tokens=0: '[{"bbox": [1, 2, 3, 4], "category": "Text", "text": "kept"}, {"bbox": [5, 6, 7, 8], "category": "Text", "text": "cut o'
     res = p.parse_file(str(img), prompt_mode="prompt_layout_all_en")
-    assert res[0].get("filtered") is True and open(res[0]["md_content_path"]).read() == "not json"
+    assert res[0].get("filtered") is True and open(res[0]["md_content_path"]).read() == "kept"      # OutputCleaner drops the unfinished cell
     with pytest.raises(ValueError):
         p.parse_file(str(tmp_path / "x.tiff"))
 

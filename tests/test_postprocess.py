@@ -52,5 +52,18 @@ def test_post_process_output_modes():
         r = L.post_process_output(c["response"], c["mode"], page, seen)
         assert isinstance(r, tuple) == c["tuple"]
         assert (list(r) if isinstance(r, tuple) else r) == c["out"], c
-    # a response that is not JSON: returned as text, flagged (the reference would run its OutputCleaner here)
-    assert L.post_process_output("not json", "prompt_layout_all_en", page, seen) == ("not json", True)
+    # a response that is not JSON goes through the OutputCleaner: nothing recoverable -> empty text, flagged
+    assert L.post_process_output("not json", "prompt_layout_all_en", page, seen) == ("", True)
+
+
+def test_output_cleaner_against_the_reference_class():
+    from dots_ocr_b200.utils.output_cleaner import OutputCleaner
+    assert len(G["cleaner"]) >= 25
+    for c in G["cleaner"]:
+        assert OutputCleaner().clean_model_output(c["in"]) == c["out"], (str(c["in"])[:120], c["out"])
+
+
+def test_post_process_output_failure_path():
+    page, seen = Image.new("RGB", (1700, 2250)), Image.new("RGB", (1708, 2240))
+    for c in G["output_fail"]:
+        assert list(L.post_process_output(c["response"], "prompt_layout_all_en", page, seen)) == c["out"], c["response"][:120]
