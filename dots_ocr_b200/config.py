@@ -103,3 +103,64 @@ def small() -> DotsConfig:
 
 
 PRESETS = {"full": full, "tiny": tiny, "small": small}
+
+
+class UnsupportedCheckpoint(ValueError):
+    """The checkpoint's config.json asks for something the sm_100a kernels do not implement."""
+
+
+def from_hf_dict(d: dict) -> DotsConfig:
+    """DotsConfig from the ``config.json`` of a HF ``weights/DotsOCR`` directory (``dots_ocr/parser.py:67``;
+    field names per ``vllm/transformers_utils/configs/dotsocr.py:12-66``: Qwen2Config at the top level,
+    ``vision_config`` nested).  Missing keys take the published defaults; options that would change the
+    arithmetic the kernels implement are refused instead of being ignored."""
+    vd = dict(d.get("vision_config") or {})
+    bad = []
+    if vd.get("use_bias", False):
+        bad.append("vision_config.use_bias=true (ViT linears are bias-free in the kernels)")
+    if not vd.get("post_norm", True):
+        bad.append("vision_config.post_norm=false")
+    if vd.get("is_causal", False):
+        bad.append("vision_config.is_causal=true")
+    if d.get("tie_word_embeddings", False):
+        bad.append("tie_word_embeddings=true (lm_head is a separate matrix)")
+    if d.get("rope_scaling") not in (None, {}) and (d["rope_scaling"] or {}).get("rope_type", "default") != "default":
+        bad.append(f"rope_scaling={d['rope_scaling']!r}")
+    if isinstance(d.get("rope_parameters"), dict) and d["rope_parameters"].get("rope_type", "default") != "default":
+        bad.append(f"rope_parameters={d['rope_parameters']!r}")
+    if d.get("use_sliding_window", False):
+        bad.append("use_sliding_window=true")
+    if d.get("hidden_act", "silu") != "silu":
+        bad.append(f"hidden_act={d.get('hidden_act')!r}")
+    vkeys = ("embed_dim", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "num_channels",
+             "patch_size", "spatial_merge_size", "temporal_patch_size", "rms_norm_eps")
+    v = VisionConfig(**{k: vd[k] for k in vkeys if k in vd})
+    heads = int(d.get("num_attention_heads", TextConfig.num_attention_heads))
+    hidden = int(d.get("hidden_size", TextConfig.hidden_size))
+    tkw = dict(hidden_size=hidden, num_attention_heads=heads, head_dim=int(d.get("head_dim") or hidden // heads))
+    for k in ("intermediate_size", "num_hidden_layers", "num_key_value_heads", "vocab_size", "rms_norm_eps", "rope_theta",
+              "max_position_embeddings"):
+        if k in d:
+            tkw[k] = d[k]
+    if "rope_theta" not in d and isinstance(d.get("rope_parameters"), dict) and "rope_theta" in d["rope_parameters"]:
+        tkw["rope_theta"] = d["rope_parameters"]["rope_theta"]      # transformers >= 5 spelling
+    t = TextConfig(**tkw)
+    if t.head_dim != 128 or v.head_dim != 128:
+        bad.append(f"head_dim {t.head_dim} (text) / {v.head_dim} (vision): the attention kernels are built for 128")
+    if v.hidden_size != t.hidden_size:
+        bad.append(f"vision_config.hidden_size {v.hidden_size} != hidden_size {t.hidden_size}")
+    if t.num_attention_heads % t.num_key_value_heads:
+        bad.append("num_attention_heads is not a multiple of num_key_value_heads")
+    if v.temporal_patch_size != 1 or v.spatial_merge_size != 2 or v.patch_size != 14 or v.num_channels != 3:
+        bad.append("patch geometry other than 3x1x14x14 with 2x2 merge")
+    if bad:
+        raise UnsupportedCheckpoint("config.json is outside what the B200 path implements: " + "; ".join(bad))
+    return DotsConfig(vision=v, text=t, image_token_id=int(d.get("image_token_id", 151665)),
+                      video_token_id=int(d.get("video_token_id", 151656)), name=str(d.get("_name_or_path") or "dots.ocr"))
+
+
+def from_hf_dir(path: str) -> DotsConfig:
+    import json
+    import os
+    with open(os.path.join(path, "config.json"), "r", encoding="utf-8") as f:
+        return from_hf_dict(json.load(f))

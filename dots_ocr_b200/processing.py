@@ -105,6 +105,79 @@ class SyntheticTokenizer:
         return bytes(int(i) for i in ids if 0 <= int(i) < 256).decode("utf-8", errors="replace")
 
 
+class HFTokenizer:
+    """The checkpoint's own tokenizer behind the interface ``PageRunner`` uses (``encode_chat`` / ``decode`` /
+    ``eos_token_id`` / ``pad_token_id`` / ``stop_ids``).
+
+    The prompt text follows the reference's two call sites: the chat template applied to a user turn whose content is
+    ``<|img|><|imgpad|><|endofimg|>{prompt}`` (``dots_ocr/model/inference.py:25-36`` with vLLM's
+    ``--chat-template-content-format string``; the HF processor renders the same string, ``parser.py:79-98``), after
+    which the single ``<|imgpad|>`` is widened to one id per merged image token, as the processor does.  When the
+    directory ships no chat template, the layout documented in SURVEY.md Appendix C is used:
+    ``<|user|>…<|endofuser|><|assistant|>``."""
+
+    IMG, PAD, END = "<|img|>", "<|imgpad|>", "<|endofimg|>"
+
+    def __init__(self, path_or_tokenizer, image_token_id: Optional[int] = None, generation_config: Optional[dict] = None):
+        if isinstance(path_or_tokenizer, str):
+            from transformers import AutoTokenizer
+            tok = AutoTokenizer.from_pretrained(path_or_tokenizer)
+            if generation_config is None:
+                import json
+                import os
+                g = os.path.join(path_or_tokenizer, "generation_config.json")
+                if os.path.isfile(g):
+                    with open(g, "r", encoding="utf-8") as f:
+                        generation_config = json.load(f)
+        else:
+            tok = path_or_tokenizer
+        self.tok = tok
+        pad = tok.convert_tokens_to_ids(self.PAD)
+        if pad is None or pad == getattr(tok, "unk_token_id", None):
+            raise ValueError("tokenizer has no <|imgpad|> token: not a dots.ocr tokenizer")
+        if image_token_id is not None and int(image_token_id) != int(pad):
+            raise ValueError(f"config image_token_id {image_token_id} != tokenizer id of <|imgpad|> {pad}")
+        self.image_token_id = int(pad)
+        # HF generate's stop set: generation_config.json's eos_token_id (int or list), else the tokenizer's eos
+        eos = (generation_config or {}).get("eos_token_id", tok.eos_token_id)
+        ids = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, (list, tuple)) else [int(eos)])
+        self.stop_ids = tuple(dict.fromkeys(ids))
+        self.eos_token_id = self.stop_ids[0] if self.stop_ids else None
+        p = (generation_config or {}).get("pad_token_id", tok.pad_token_id)
+        self.pad_token_id = int(p) if p is not None else (self.eos_token_id if self.eos_token_id is not None else 0)
+        self._cache = {}
+
+    def render(self, prompt: str) -> str:
+        content = f"{self.IMG}{self.PAD}{self.END}{prompt}"
+        if getattr(self.tok, "chat_template", None):
+            return self.tok.apply_chat_template([{"role": "user", "content": content}], tokenize=False,
+                                                add_generation_prompt=True)
+        return f"<|user|>{content}<|endofuser|><|assistant|>"
+
+    def encode_chat(self, prompt: str, n_image_tokens: int) -> List[int]:
+        halves = self._cache.get(prompt)
+        if halves is None:
+            text = self.render(prompt)
+            if text.count(self.PAD) != 1:
+                raise ValueError("the rendered prompt must contain exactly one <|imgpad|> (one image per page)")
+            before, after = text.split(self.PAD)
+            # <|imgpad|> is a special token, so tokenising either side of it separately equals tokenising the whole
+            halves = (self.tok.encode(before, add_special_tokens=False), self.tok.encode(after, add_special_tokens=False))
+            if len(self._cache) < 64:
+                self._cache[prompt] = halves
+        return list(halves[0]) + [self.image_token_id] * int(n_image_tokens) + list(halves[1])
+
+    def decode(self, ids: Sequence[int]) -> str:
+        """``processor.batch_decode(..., skip_special_tokens=True, clean_up_tokenization_spaces=False)``
+        (parser.py:114-116), cut at the first stop id."""
+        ids = [int(i) for i in ids]
+        for k, i in enumerate(ids):
+            if i in self.stop_ids:
+                ids = ids[:k]
+                break
+        return self.tok.decode(ids, skip_special_tokens=True, clean_up_tokenization_spaces=False)
+
+
 def build_text_inputs(tokenizer: SyntheticTokenizer, n_image_tokens: Sequence[int], prompts: Sequence[str]):
     """Left-padded input_ids + attention_mask for prompts whose images contribute `n_image_tokens[i]` <|imgpad|> slots."""
     rows = [tokenizer.encode_chat(prompt, n) for prompt, n in zip(prompts, n_image_tokens)]

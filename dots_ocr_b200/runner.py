@@ -29,14 +29,33 @@ class PageRunner:
     @classmethod
     def from_default(cls, device: str = "cuda:0", weights_dir: str = "./weights/DotsOCR", preset: Optional[str] = None):
         """Real checkpoint if ``./weights/DotsOCR`` exists (parser.py:67), else the seeded synthetic one."""
+        if os.path.isdir(weights_dir):
+            return cls.from_checkpoint(weights_dir, device)
         from .engine import Engine
         preset = preset or os.environ.get("DOTS_B200_PRESET", "full")
         cfg = _config.PRESETS[preset]()
-        if os.path.isdir(weights_dir):
-            ckpt = _weights.load_safetensors_dir(weights_dir, device=device)
-        else:
-            ckpt = _weights.make_synthetic_checkpoint(cfg, 0, "peaked", device=device)
+        ckpt = _weights.make_synthetic_checkpoint(cfg, 0, "peaked", device=device)
         return cls(Engine(cfg, ckpt, device), SyntheticTokenizer(cfg))
+
+    @classmethod
+    def from_checkpoint(cls, weights_dir: str, device: str = "cuda:0", engine_factory=None):
+        """A HF ``weights/DotsOCR`` directory: ``config.json`` -> DotsConfig (unsupported options refused),
+        ``*.safetensors`` -> HBM (validated against the config), tokenizer + ``generation_config.json`` -> HFTokenizer.
+        A directory with tensors only (no config / tokenizer files) runs with the published architecture and the
+        byte-level stand-in tokenizer."""
+        cfg = _config.from_hf_dir(weights_dir) if os.path.isfile(os.path.join(weights_dir, "config.json")) else _config.full()
+        ckpt = _weights.load_safetensors_dir(weights_dir, device=device)
+        _weights.validate_checkpoint(cfg, ckpt)
+        has_tok = any(os.path.isfile(os.path.join(weights_dir, f)) for f in ("tokenizer.json", "tokenizer_config.json", "vocab.json"))
+        if has_tok:
+            from .processing import HFTokenizer
+            tokenizer = HFTokenizer(weights_dir, image_token_id=cfg.image_token_id)
+        else:
+            tokenizer = SyntheticTokenizer(cfg)
+        if engine_factory is None:
+            from .engine import Engine
+            engine_factory = Engine
+        return cls(engine_factory(cfg, ckpt, device), tokenizer)
 
     def infer_batch(self, images: Sequence, prompts: Sequence[str], max_new_tokens: int = 512, gpu_preprocess: bool = True,
                     budgets: Optional[Sequence[int]] = None) -> List[str]:

@@ -156,3 +156,42 @@ def load_safetensors_dir(path: str, device: str | torch.device = "cpu",
                 name = k.replace(".attn.qkv_proj.", ".attn.qkv.").replace(".attn.out_proj.", ".attn.proj.")
                 out[name] = sf.get_tensor(k).to(dtype)
     return out
+
+
+def validate_checkpoint(cfg: DotsConfig, ckpt: Dict[str, torch.Tensor], allow_extra: bool = True) -> None:
+    """Every tensor the engine will read exists with the shape ``cfg`` implies; raise ``ValueError`` naming the
+    first few offenders otherwise (a silent mis-shape would surface as a wrong pitch inside a kernel)."""
+    missing, wrong = [], []
+    expected = set()
+    for name, shape, _ in _specs(cfg):
+        expected.add(name)
+        w = ckpt.get(name)
+        if w is None:
+            missing.append(name)
+        elif tuple(w.shape) != tuple(shape):
+            wrong.append(f"{name}: {tuple(w.shape)} != {tuple(shape)}")
+    extra = [] if allow_extra else sorted(k for k in ckpt if k not in expected)
+    if missing or wrong or extra:
+        def head(xs):
+            return ", ".join(xs[:6]) + (f", ... (+{len(xs) - 6})" if len(xs) > 6 else "")
+        parts = []
+        if missing:
+            parts.append(f"{len(missing)} missing [{head(missing)}]")
+        if wrong:
+            parts.append(f"{len(wrong)} mis-shaped [{head(wrong)}]")
+        if extra:
+            parts.append(f"{len(extra)} unexpected [{head(extra)}]")
+        raise ValueError("checkpoint does not match the configuration: " + "; ".join(parts))
+
+
+def save_safetensors_dir(ckpt: Dict[str, torch.Tensor], path: str, shards: int = 1) -> None:
+    """Write ``ckpt`` as ``model-0000i-of-0000n.safetensors`` files (test / tooling helper: the inverse of
+    ``load_safetensors_dir``)."""
+    from safetensors.torch import save_file
+    os.makedirs(path, exist_ok=True)
+    names = list(ckpt)
+    per = (len(names) + shards - 1) // shards
+    for i in range(shards):
+        part = {k: ckpt[k].contiguous() for k in names[i * per:(i + 1) * per]}
+        if part:
+            save_file(part, os.path.join(path, f"model-{i + 1:05d}-of-{shards:05d}.safetensors"))
