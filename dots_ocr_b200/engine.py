@@ -36,6 +36,50 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def stop_list(eos_token_id) -> List[int]:
+    """``eos_token_id`` as HF accepts it (None, an int, or a list of ints) -> ordered, de-duplicated list."""
+    if eos_token_id is None:
+        return []
+    if isinstance(eos_token_id, (list, tuple)):
+        return list(dict.fromkeys(int(e) for e in eos_token_id))
+    if isinstance(eos_token_id, torch.Tensor):
+        return list(dict.fromkeys(int(e) for e in eos_token_id.reshape(-1).tolist()))
+    return [int(eos_token_id)]
+
+
+def finalize_new_tokens(out_new: torch.Tensor, stops: List[int], pad: int) -> torch.Tensor:
+    """The generated block [B, N] the way HF's greedy loop leaves it: everything after a row's first stop id is
+    ``pad``, and the block ends at the step where the last row stopped (``GenerationMixin._sample``: finished rows
+    keep emitting pad, the loop ends once every row has finished).  The decode kernels pad after the PRIMARY stop id
+    (``stops[0]``) on the device; secondary ids are handled here."""
+    if not stops:
+        return out_new
+    hit = out_new == stops[0]
+    for s in stops[1:]:
+        hit |= out_new == s
+    has = hit.any(dim=1)
+    fin_step = hit.int().argmax(dim=1)
+    if len(stops) > 1:
+        col = torch.arange(out_new.shape[1], device=out_new.device).unsqueeze(0)
+        after = has.unsqueeze(1) & (col > fin_step.unsqueeze(1))
+        out_new = torch.where(after, torch.full_like(out_new, int(pad)), out_new)
+    if bool(has.all()):
+        out_new = out_new[:, : int(fin_step.max().item()) + 1]      # HF stops once every row has finished
+    return out_new
+
+
+def replay_steps(launch, n: int, every: int, all_finished) -> int:
+    """Run ``launch()`` up to ``n`` times; after every ``every`` launches (0 = never) ask ``all_finished()`` (one
+    device->host read of the finished flags) and stop early when it says so.  Returns the launches made."""
+    done = 0
+    while done < n:
+        launch()
+        done += 1
+        if every and done % every == 0 and done < n and all_finished():
+            break
+    return done
+
+
 @dataclass
 class GenerateOutput:
     sequences: torch.Tensor                 # [B, T + N] int64 (prompt included, HF layout)
@@ -111,6 +155,7 @@ class Engine:
         # exposed epilogues cost what the PDL-overlapped kernel boundaries cost, and it blocks the attention kernel's early
         # KV prefetch) -- kept as an opt-in experiment, see DESIGN.md section 8.
         self.decode_chain = False
+        self.eos_check_every = 64       # decode steps between looks at the finished flags (only when a stop id is given)
 
     # ------------------------------------------------------------------------------ vision
     @torch.no_grad()
@@ -278,8 +323,8 @@ class Engine:
         t = self.cfg.text
         dev = self.device
         H = t.hidden_size
-        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, eos=-1 if eos_token_id is None else int(eos_token_id),
-                  pad=int(pad_token_id))
+        stops = stop_list(eos_token_id)
+        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, eos=stops[0] if stops else -1, pad=int(pad_token_id))
         pl = st["plan"]
         max_part = max(pl["qkv"] * (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim, pl["o"] * H, pl["down"] * H)
         st["partial"] = torch.empty(max_part * B, device=dev, dtype=torch.float32)
@@ -328,7 +373,7 @@ class Engine:
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                  pixel_values: Optional[torch.Tensor] = None, image_grid_thw=None, max_new_tokens: int = 16,
-                 eos_token_id: Optional[int] = None, pad_token_id: int = 0, forced_ids: Optional[torch.Tensor] = None,
+                 eos_token_id=None, pad_token_id: int = 0, forced_ids: Optional[torch.Tensor] = None,
                  return_logits: bool = False, use_graph: bool = True, image_embeds: Optional[torch.Tensor] = None,
                  pages_u8=None, **unused) -> GenerateOutput:
         """HF-shaped greedy generation: returns ids [B, T + N'] including the prompt (parser.py:110-113)."""
@@ -385,6 +430,12 @@ class Engine:
 
         n_steps = N - 1
         per_step = self.launches_per_decode_step(B)
+        # with a stop id, look at the finished flags every `eos_check_every` steps and leave once every page is done
+        check = int(self.eos_check_every) if st["eos"] >= 0 else 0
+
+        def all_finished() -> bool:
+            return bool(st["finished"].all().item())
+
         prof_ev = None
         if ops.PROFILE is not None and n_steps > 0:
             prof_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -408,28 +459,27 @@ class Engine:
                             with g:
                                 self._decode_step(st)
                         # capture does not execute: replay for every remaining step
-                        for _ in range(n_steps - 1):
-                            g.launch()
+                        done += replay_steps(g.launch, n_steps - 1, check, all_finished)
                     torch.cuda.current_stream().wait_stream(cap)
-                    done = n_steps
                 self.launches += per_step * done
                 st["_graph"] = None
             else:
+                done = 0
                 for s in range(n_steps):
                     self._decode_step(st)
+                    done += 1
                     if return_logits:
                         all_logits[s + 1].copy_(st["logits"])
-                self.launches += per_step * n_steps
+                    if check and done % check == 0 and done < n_steps and all_finished():
+                        break
+                self.launches += per_step * done
 
         if prof_ev is not None:
             prof_ev[1].record()
             ops.PROFILE.append(("decode_phase", self.decode_bytes(B, seq_lens, n_steps), prof_ev[0], prof_ev[1]))
-        out_new = st["out_ids"]
-        if eos_token_id is not None:
-            fin_step = (out_new == int(eos_token_id)).int().argmax(dim=1)
-            has = (out_new == int(eos_token_id)).any(dim=1)
-            if bool(has.all()):
-                out_new = out_new[:, : int(fin_step.max().item()) + 1]      # HF stops once every row has finished
+        out_new = finalize_new_tokens(st["out_ids"], stop_list(eos_token_id), int(pad_token_id))
         seqs = torch.cat([ids, out_new], dim=1)
+        if return_logits and out_new.shape[1] < N:
+            all_logits = all_logits[: out_new.shape[1]]
         return GenerateOutput(sequences=seqs, logits=all_logits.transpose(0, 1) if return_logits else None,
                               image_embeds=image_embeds)

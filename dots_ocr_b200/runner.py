@@ -72,8 +72,10 @@ class PageRunner:
             dev = self.engine.device
             kw = dict(pages_u8=[p.to(dev, non_blocking=True) for p in pages]) if gpu_preprocess else \
                 dict(pixel_values=inputs["pixel_values"].to(dev), image_grid_thw=inputs["image_grid_thw"])
+            # every stop id of the checkpoint's generation config when the tokenizer knows them (HF accepts a list too)
+            stops = list(getattr(self.tokenizer, "stop_ids", ())) or self.tokenizer.eos_token_id
             out = self.engine.generate(input_ids=inputs["input_ids"].to(dev), attention_mask=inputs["attention_mask"].to(dev),
-                                       max_new_tokens=n_new, eos_token_id=self.tokenizer.eos_token_id,
+                                       max_new_tokens=n_new, eos_token_id=stops,
                                        pad_token_id=self.tokenizer.pad_token_id, **kw)
             seq = out.sequences.cpu()
         T = inputs["input_ids"].shape[1]

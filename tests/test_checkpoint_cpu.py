@@ -165,7 +165,7 @@ class _RecordingEngine:
         new = torch.full((B, max_new_tokens), pad_token_id, dtype=torch.int64)
         reply = self.reply
         new[:, :len(reply)] = torch.tensor(reply)
-        new[:, len(reply)] = eos_token_id
+        new[:, len(reply)] = eos_token_id[0] if isinstance(eos_token_id, list) else eos_token_id
         from types import SimpleNamespace
         return SimpleNamespace(sequences=torch.cat([input_ids, new], dim=1))
 
@@ -191,7 +191,7 @@ def test_page_runner_from_checkpoint_directory(tmp_path):
     img = Image.new("RGB", (120, 90), (255, 255, 255))
     texts = runner.infer_batch([img, img], ["p1", "p2"], max_new_tokens=128, gpu_preprocess=False)
     assert texts == ['[{"bbox": [1, 2, 3, 4], "category": "Text", "text": "ok"}]'] * 2
-    assert eng.calls[0]["eos"] == fast.eos_token_id and eng.calls[0]["n"] == 128
+    assert eng.calls[0]["eos"] == [fast.eos_token_id] and eng.calls[0]["n"] == 128
     assert "pixel_values" in eng.calls[0]["keys"] and "image_grid_thw" in eng.calls[0]["keys"]
 
     # a directory whose tensors do not fit its config.json is refused before any engine is built

@@ -324,3 +324,60 @@ def test_batching_runner_groups_concurrent_callers():
     with pytest.raises(ValueError):
         br2.infer("a", "b")
     br2.close()
+
+
+# ------------------------------------------------------------------ stop ids / early exit (host half of generate)
+def test_finalize_new_tokens_equals_hf_generate_with_several_stop_ids():
+    """finalize_new_tokens applied to the un-stopped greedy continuation must give what HF's own generate returns when
+    it is handed the same eos list and pad id (rows are independent under left padding)."""
+    from dots_ocr_b200 import config, weights
+    from dots_ocr_b200.engine import finalize_new_tokens, stop_list
+    from oracle.model import build_qwen2
+    cfg = config.tiny()
+    m = build_qwen2(cfg.text, weights.make_synthetic_checkpoint(cfg, 0, "random"), torch.float32, torch.device("cpu"))
+    T, N, pad = 7, 12, 0
+    ids = torch.randint(1, 2000, (3, T), generator=torch.Generator().manual_seed(11))
+    kw = dict(do_sample=False, pad_token_id=pad, attention_mask=torch.ones_like(ids))
+    with torch.no_grad():
+        raw = m.generate(input_ids=ids, max_new_tokens=N, min_new_tokens=N, **kw)[:, T:]
+        assert raw.shape == (3, N)
+        cases = [
+            [int(raw[0, 3]), int(raw[1, 5]), int(raw[2, 2])],      # every row stops, at different steps, on different ids
+            [int(raw[0, 3]), int(raw[1, 5])],                      # one row never stops: no trimming, two rows padded
+            [int(raw[2, 0])],                                      # single id, first token
+            [5000],                                                # never produced
+        ]
+        for stops in cases:
+            want = m.generate(input_ids=ids, max_new_tokens=N, eos_token_id=stops, **kw)[:, T:]
+            got = raw.clone()
+            # the device pads after the primary stop id; emulate that before the host finalisation
+            prim = (got == stops[0])
+            first = torch.where(prim.any(1), prim.int().argmax(1), torch.full((3,), N))
+            got = torch.where(torch.arange(N)[None, :] > first[:, None], torch.full_like(got, pad), got)
+            got = finalize_new_tokens(got, stop_list(stops), pad)
+            assert torch.equal(got, want), (stops, got, want)
+    assert stop_list(None) == [] and stop_list(7) == [7] and stop_list([7, 9, 7]) == [7, 9]
+    assert stop_list(torch.tensor([3, 4])) == [3, 4]
+    assert finalize_new_tokens(raw, [], pad) is raw
+
+
+def test_replay_steps_checks_every_k_and_stops_early():
+    from dots_ocr_b200.engine import replay_steps
+    log = []
+    assert replay_steps(lambda: log.append("L"), 10, 0, lambda: log.append("C") or True) == 10
+    assert log == ["L"] * 10                                        # every=0: never asks
+    log.clear()
+    done_at = {"n": 0}
+
+    def finished():
+        log.append("C")
+        return log.count("L") >= done_at["n"]
+
+    done_at["n"] = 7
+    assert replay_steps(lambda: log.append("L"), 20, 4, finished) == 8      # asked at 4 (no) and 8 (yes)
+    assert log.count("C") == 2
+    log.clear()
+    done_at["n"] = 100
+    assert replay_steps(lambda: log.append("L"), 8, 4, finished) == 8       # no question after the last launch
+    assert log.count("C") == 1
+    assert replay_steps(lambda: None, 0, 4, lambda: True) == 0
