@@ -62,3 +62,14 @@ def token_counts(height: int, width: int, patch: int = 14, merge: int = 2, **kw)
     """(ViT tokens, LLM image tokens) for an image of the given size."""
     gh, gw = vit_grid(height, width, patch, **kw)
     return gh * gw, (gh * gw) // (merge * merge)
+
+
+def PILimage_to_base64(image, format: str = "PNG") -> str:
+    """``data:image/<fmt>;base64,...`` URL of a PIL image: what the reference's HTTP client puts in ``image_url``
+    (``dots_ocr/utils/image_utils.py:64-68``) and what ``dots_ocr_b200.server`` accepts."""
+    import base64
+    import io
+    with io.BytesIO() as buf:
+        image.save(buf, format=format)
+        payload = base64.b64encode(buf.getvalue()).decode("ascii")
+    return "data:image/" + format.lower() + ";base64," + payload
