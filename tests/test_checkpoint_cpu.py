@@ -200,3 +200,47 @@ def test_page_runner_from_checkpoint_directory(tmp_path):
         json.dump(hf_cfg, f)
     with pytest.raises(ValueError, match="missing"):
         PageRunner.from_checkpoint(str(tmp_path), device="cpu", engine_factory=_RecordingEngine)
+
+
+def test_fabricated_checkpoint_directory_loads_everywhere(tmp_path):
+    """tools/make_checkpoint_dir.py (tiny preset): our loader, the stock HF image processor and vLLM's DotsOCRConfig all read
+    it; its tokenizer assigns the ids processing.SyntheticTokenizer uses, so both tokenizers drive the engine identically."""
+    import importlib.util
+    from dots_ocr_b200.processing import SyntheticTokenizer
+    from dots_ocr_b200.runner import PageRunner
+    spec = importlib.util.spec_from_file_location("make_checkpoint_dir",
+                                                  os.path.join(os.path.dirname(__file__), "..", "tools", "make_checkpoint_dir.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    cfg = C.tiny()
+    out = str(tmp_path / "DotsOCR")
+    info = tool.write_dir(cfg, out, seed=5, flavour="peaked", shards=3)
+    assert info["tensors"] == len(W.tensor_names(cfg))
+
+    runner = PageRunner.from_checkpoint(out, device="cpu", engine_factory=_RecordingEngine)
+    got = runner.engine.cfg
+    assert (got.text, got.vision, got.image_token_id, got.video_token_id) == (cfg.text, cfg.vision, cfg.image_token_id,
+                                                                              cfg.video_token_id)
+    want = W.make_synthetic_checkpoint(cfg, 5, "peaked")
+    assert all(torch.equal(runner.engine.ckpt[k], want[k]) for k in want)
+    tk, st = runner.tokenizer, SyntheticTokenizer(cfg)
+    prompt = "Please output: ünïcode ✓ 表格\n\t{}[]"
+    assert tk.encode_chat(prompt, 9) == st.encode_chat(prompt, 9)
+    assert tk.decode(list(prompt.encode())) == prompt == st.decode(list(prompt.encode()))
+    sp = info["special_tokens"]
+    assert tk.stop_ids == (sp["<|endofassistant|>"], sp["<|endoftext|>"]) and tk.pad_token_id == sp["<|endoftext|>"]
+    with open(os.path.join(out, "model.safetensors.index.json")) as f:
+        index = json.load(f)
+    assert set(index["weight_map"]) == set(want) and set(index["weight_map"].values()) == \
+        {f for f in os.listdir(out) if f.endswith(".safetensors")}
+
+    from transformers import Qwen2VLImageProcessor
+    ip = Qwen2VLImageProcessor.from_pretrained(out)
+    assert (ip.patch_size, ip.merge_size, ip.size["shortest_edge"], ip.size["longest_edge"]) == (14, 2, 3136, 11289600)
+    try:
+        from vllm.transformers_utils.configs.dotsocr import DotsOCRConfig
+    except Exception:
+        return
+    vc = DotsOCRConfig.from_pretrained(out)
+    assert vc.vision_config.embed_dim == cfg.vision.embed_dim and vc.image_token_id == cfg.image_token_id
+    assert vc.num_key_value_heads == cfg.text.num_key_value_heads and vc.architectures == ["DotsOCRForCausalLM"]
