@@ -1,8 +1,7 @@
 """Stop ids and early exit of the decode loop on the device (tiny config, `peaked` checkpoint: the next token is a
 known permutation of the previous one, so the step at which each row stops is chosen by the test).
 
-Sorted last on purpose: these cases were added after the round's GPU budget was spent and have only run on CPU stand-ins
-(tests/test_cpu_host.py: finalize_new_tokens vs HF generate, replay_steps)."""
+The host halves (finalize_new_tokens vs HF generate, replay_steps) are pinned on CPU in tests/test_cpu_host.py."""
 import pytest
 import torch
 
