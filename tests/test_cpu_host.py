@@ -326,6 +326,48 @@ def test_batching_runner_groups_concurrent_callers():
     br2.close()
 
 
+def test_batching_runner_closes_a_batch_on_the_vit_token_budget():
+    """Pages are grouped up to a ViT-token budget: four 1024x1024 pages (5476 tokens each) fit 22 000, the 1960x1960 page
+    (19 600) opens its own batch, and order of results is per caller."""
+    import time
+    from PIL import Image
+    from dots_ocr_b200.batching import BatchingRunner, page_vit_tokens
+
+    class FakeRunner:
+        min_pixels = max_pixels = None
+
+        def __init__(self):
+            self.calls = []
+
+        def infer_batch(self, images, prompts, max_new_tokens=512):
+            self.calls.append([im.size for im in images])
+            time.sleep(0.02)
+            return [f"{im.size[0]}:{pr}" for im, pr in zip(images, prompts)]
+
+    small, big = Image.new("RGB", (1024, 1024)), Image.new("RGB", (1960, 1960))
+    assert page_vit_tokens(small) == 5476 and page_vit_tokens(big) == 19600 and page_vit_tokens("not an image") == 0
+    assert page_vit_tokens(Image.new("RGB", (10000, 10))) == 0          # aspect ratio > 200: left for the runner to refuse
+    fake = FakeRunner()
+    br = BatchingRunner(fake, max_batch=64, max_wait_ms=200, max_batch_tokens=22000)
+    futs = [br.submit(im, f"p{i}") for i, im in enumerate([small, small, small, big, small, small])]
+    got = [f.result(timeout=20) for f in futs]
+    br.close()
+    assert got == ["1024:p0", "1024:p1", "1024:p2", "1960:p3", "1024:p4", "1024:p5"]
+    assert [len(c) for c in fake.calls] == [3, 1, 2] and fake.calls[1] == [(1960, 1960)], fake.calls
+    # the wait for stragglers is counted from the first request, not restarted by every arrival
+    fake2 = FakeRunner()
+    br2 = BatchingRunner(fake2, max_batch=64, max_wait_ms=150)
+    t0 = time.monotonic()
+    f0 = br2.submit(small, "a")
+    for k in range(4):
+        time.sleep(0.06)
+        br2.submit(small, f"late{k}")
+    f0.result(timeout=20)
+    assert time.monotonic() - t0 < 0.6
+    br2.close()
+    assert sum(len(c) for c in fake2.calls) == 5 and len(fake2.calls[0]) < 5
+
+
 # ------------------------------------------------------------------ stop ids / early exit (host half of generate)
 def test_finalize_new_tokens_equals_hf_generate_with_several_stop_ids():
     """finalize_new_tokens applied to the un-stopped greedy continuation must give what HF's own generate returns when
