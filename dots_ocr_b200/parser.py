@@ -5,9 +5,11 @@ The hot-path seam is re-implemented here (``_load_hf_model`` / ``_inference_with
 ``get_prompt`` / ``parse_image`` / ``parse_file``) together with the post-decode CPU pipeline of
 ``_parse_single_image`` (``parser.py:143-253``): the decoded layout JSON is mapped back to page coordinates and
 rendered to Markdown by ``utils/layout_utils.py`` / ``utils/format_transformer.py``, whose behaviour is pinned against
-the reference functions, JSON repair of cut-off responses included (``tests/test_postprocess.py``).  Not reproduced: drawing
-the layout on the page and PDF rasterisation (both PyMuPDF).  See INTEGRATION.md for patching the reference's own
-parser instead.
+the reference functions, JSON repair of cut-off responses included (``tests/test_postprocess.py``).  Multi-page inputs fan
+out over ``num_thread`` threads like the reference's ``parse_pdf`` (``parser.py:261-297``); the threads meet in the request
+batcher, so the pages of one document share ``generate`` calls.  PDF rasterisation needs PyMuPDF (``utils/doc_utils.py``;
+not in this image -- ``parse_pages`` takes pre-rasterised page images).  Not reproduced: drawing the layout on the page.
+See INTEGRATION.md for patching the reference's own parser instead.
 """
 from __future__ import annotations
 
@@ -97,7 +99,8 @@ class DotsOCRParser:
             image = image.resize((rw, rh))
         return image
 
-    def _parse_single_image(self, origin_image, prompt_mode, save_dir, save_name, source="image", page_idx=0, bbox=None):
+    def _parse_single_image(self, origin_image, prompt_mode, save_dir, save_name, source="image", page_idx=0, bbox=None,
+                            fitz_preprocess=False):
         """One page: prompt -> model -> layout cells in page coordinates (.json) + Markdown (.md, _nohf.md), as the reference
         writes them (parser.py:143-253).  The page image is saved undecorated as <name>.jpg (no PyMuPDF drawing)."""
         from .utils.layout_utils import post_process_output
@@ -110,7 +113,11 @@ class DotsOCRParser:
             assert min_pixels >= MIN_PIXELS, f"min_pixels should >= {MIN_PIXELS}"
         if max_pixels is not None:
             assert max_pixels <= MAX_PIXELS, f"max_pixels should <= {MAX_PIXELS}"
-        image = self._fetch_image(origin_image, min_pixels, max_pixels)
+        if source == 'image' and fitz_preprocess:
+            from .utils.doc_utils import get_image_by_fitz_doc          # re-render at self.dpi (parser.py:161-163)
+            image = self._fetch_image(get_image_by_fitz_doc(origin_image, target_dpi=self.dpi), min_pixels, max_pixels)
+        else:
+            image = self._fetch_image(origin_image, min_pixels, max_pixels)
         input_height, input_width = smart_resize(image.height, image.width)
         prompt = self.get_prompt(prompt_mode, bbox, origin_image, image, min_pixels=min_pixels, max_pixels=max_pixels)
         response = self._inference_with_hf(image, prompt) if self.use_hf else self._inference_with_vllm(image, prompt)
@@ -150,18 +157,37 @@ class DotsOCRParser:
             result['md_content_path'] = md_path
         return result
 
-    def parse_image(self, input_path, filename, prompt_mode, save_dir, bbox=None):
+    def parse_image(self, input_path, filename, prompt_mode, save_dir, bbox=None, fitz_preprocess=False):
         from PIL import Image
         origin_image = input_path if isinstance(input_path, Image.Image) else Image.open(input_path)
-        result = self._parse_single_image(origin_image, prompt_mode, save_dir, filename, source="image", bbox=bbox)
+        result = self._parse_single_image(origin_image, prompt_mode, save_dir, filename, source="image", bbox=bbox,
+                                          fitz_preprocess=fitz_preprocess)
         result['file_path'] = input_path if isinstance(input_path, str) else filename
         return [result]
 
-    def parse_pdf(self, input_path, filename, prompt_mode, save_dir):
-        raise NotImplementedError("PDF rasterisation (PyMuPDF, dots_ocr/utils/doc_utils.py:42-60) is outside the hot-path "
-                                  "scope; rasterise pages to images and call parse_image")
+    def parse_pages(self, images, filename, prompt_mode, save_dir, file_path=None):
+        """The pages of one document (PIL images, in order) -> one result per page, sorted by ``page_no``; outputs are named
+        ``<filename>_page_<i>.*`` as for a PDF (parser.py:261-297).  Up to ``num_thread`` pages are in flight at once, in
+        both modes: the threads block in the request batcher, which is what turns a document into batched ``generate``
+        calls (the reference drops to one thread under ``use_hf`` because the HF model object is not re-entrant)."""
+        from multiprocessing.pool import ThreadPool
+        images = list(images)
+        if not images:
+            return []
+        tasks = [dict(origin_image=im, prompt_mode=prompt_mode, save_dir=save_dir, save_name=filename, source="pdf", page_idx=i)
+                 for i, im in enumerate(images)]
+        with ThreadPool(max(1, min(len(tasks), int(self.num_thread)))) as pool:
+            results = list(pool.imap_unordered(lambda kw: self._parse_single_image(**kw), tasks))
+        results.sort(key=lambda r: r["page_no"])
+        for r in results:
+            r['file_path'] = file_path if file_path is not None else filename
+        return results
 
-    def parse_file(self, input_path, output_dir="", prompt_mode="prompt_layout_all_en", bbox=None):
+    def parse_pdf(self, input_path, filename, prompt_mode, save_dir):
+        from .utils.doc_utils import load_images_from_pdf
+        return self.parse_pages(load_images_from_pdf(input_path, dpi=self.dpi), filename, prompt_mode, save_dir, file_path=input_path)
+
+    def parse_file(self, input_path, output_dir="", prompt_mode="prompt_layout_all_en", bbox=None, fitz_preprocess=False):
         output_dir = os.path.abspath(output_dir or self.output_dir)
         filename, file_ext = os.path.splitext(os.path.basename(input_path))
         save_dir = os.path.join(output_dir, filename)
@@ -169,7 +195,7 @@ class DotsOCRParser:
         if file_ext == '.pdf':
             results = self.parse_pdf(input_path, filename, prompt_mode, save_dir)
         elif file_ext in image_extensions:
-            results = self.parse_image(input_path, filename, prompt_mode, save_dir, bbox=bbox)
+            results = self.parse_image(input_path, filename, prompt_mode, save_dir, bbox=bbox, fitz_preprocess=fitz_preprocess)
         else:
             raise ValueError(f"file extension {file_ext} not supported, supported extensions are {image_extensions} and pdf")
         with open(os.path.join(output_dir, os.path.basename(filename) + '.jsonl'), 'w', encoding='utf-8') as w:

@@ -238,6 +238,98 @@ def test_parser_plumbing_with_a_fake_runner(tmp_path):
         p.parse_file(str(tmp_path / "x.tiff"))
 
 
+class _FakeFitz:
+    """Stand-in for PyMuPDF: a "PDF" is a list of (width_pt, height_pt) page sizes; rendering scales them by the matrix."""
+
+    def __init__(self, pages):
+        import types
+        self.pages = pages
+        self.renders = []
+        fz = self
+
+        class Matrix:
+            def __init__(self, a, b):
+                self.a, self.b = a, b
+
+        class Page:
+            def __init__(self, idx, wh):
+                self.idx, self.wh = idx, wh
+
+            def get_pixmap(self, matrix, alpha=False):
+                w, h = int(self.wh[0] * matrix.a), int(self.wh[1] * matrix.b)
+                fz.renders.append((self.idx, matrix.a))
+                return types.SimpleNamespace(width=w, height=h, samples=bytes([self.idx * 40 % 256]) * (w * h * 3))
+
+        class Doc:
+            page_count = len(pages)
+
+            def __getitem__(self, i):
+                return Page(i, pages[i])
+
+            def __enter__(self):
+                return self
+
+            def __exit__(self, *a):
+                return False
+
+        self.module = types.ModuleType("fitz")
+        self.module.Matrix = Matrix
+        self.module.open = lambda *a, **k: Doc()
+
+
+def test_pdf_pages_fan_out_into_the_runner(tmp_path, monkeypatch):
+    """parse_file on a .pdf: pages rendered at dpi (72 dpi when the render would pass 4500 px), fanned out over threads,
+    results ordered by page, outputs named <file>_page_<i>.*, and the jsonl index written (parser.py:261-322)."""
+    import json as _json
+    import sys
+    import threading
+    from dots_ocr_b200 import DotsOCRParser
+    from dots_ocr_b200.utils import doc_utils
+
+    if "fitz" not in sys.modules:
+        monkeypatch.setitem(sys.modules, "fitz", None)                # "import fitz" -> ImportError
+        monkeypatch.setitem(sys.modules, "pymupdf", None)
+        with pytest.raises(doc_utils.RasteriserUnavailable, match="parse_pages"):
+            doc_utils.load_images_from_pdf("whatever.pdf")
+
+    fz = _FakeFitz([(200, 300), (300, 200), (2000, 1000), (100, 100), (120, 80)])
+    monkeypatch.setitem(sys.modules, "fitz", fz.module)
+    imgs = doc_utils.load_images_from_pdf("doc.pdf", dpi=144)
+    assert [im.size for im in imgs] == [(400, 600), (600, 400), (4000, 2000), (200, 200), (240, 160)]   # 4000 px wide: still under 4500
+    fz.renders.clear()
+    imgs = doc_utils.load_images_from_pdf("doc.pdf", dpi=216, start_page_id=1, end_page_id=2)
+    assert [im.size for im in imgs] == [(900, 600), (2000, 1000)]            # page 2 at 216 dpi = 6000 px -> native 72 dpi
+    assert fz.renders == [(1, 3.0), (2, 3.0), (2, 1.0)]
+    assert len(doc_utils.load_images_from_pdf("doc.pdf", end_page_id=99)) == 5
+
+    class Fake:
+        def __init__(self):
+            self.lock, self.seen, self.live, self.peak = threading.Lock(), [], 0, 0
+
+        def infer(self, image, prompt, max_new_tokens=0):
+            import time
+            with self.lock:
+                self.live += 1
+                self.peak = max(self.peak, self.live)
+                self.seen.append(image.size)
+            time.sleep(0.05)
+            with self.lock:
+                self.live -= 1
+            return '[{"bbox": [0, 0, 10, 10], "category": "Text", "text": "w%d"}]' % image.size[0]
+    fake = Fake()
+    p = DotsOCRParser(output_dir=str(tmp_path), runner=fake, num_thread=4, dpi=144)
+    res = p.parse_file("/somewhere/report.pdf")
+    assert [r["page_no"] for r in res] == [0, 1, 2, 3, 4] and all(r["file_path"] == "/somewhere/report.pdf" for r in res)
+    assert sorted(fake.seen) == sorted([(400, 600), (600, 400), (4000, 2000), (200, 200), (240, 160)])
+    assert 2 <= fake.peak <= 4                                           # pages in flight together, capped by num_thread
+    for i, r in enumerate(res):
+        assert r["layout_info_path"].endswith(f"report_page_{i}.json") and os.path.exists(r["md_content_path"])
+    assert open(res[2]["md_content_path"]).read() == "w4000"
+    lines = open(tmp_path / "report.jsonl").read().splitlines()
+    assert [_json.loads(ln)["page_no"] for ln in lines] == [0, 1, 2, 3, 4]
+    assert p.parse_pages([], "empty", "prompt_layout_all_en", str(tmp_path)) == []
+
+
 # ------------------------------------------------------------------ C ABI surface (no GPU compute)
 def test_library_exports_every_declared_symbol():
     from dots_ocr_b200 import _lib
