@@ -3,6 +3,7 @@ import ctypes
 import inspect
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -122,6 +123,39 @@ def test_oracle_matches_golden_vectors():
                 for _ in range(N_NEW):
                     chain.append(weights.peaked_next_token(cfg, chain[-1]))
                 assert seq[b, T:].tolist() == chain[1:]
+
+
+def test_vision_oracle_matches_vllm_own_vision_tower():
+    """oracle/vision.py against vectors produced by vLLM's DotsVisionTransformer itself, run on CPU in fp32 on the same
+    seeded weights and inputs (tests/golden/make_vllm_vision_golden.py): patch embed, every block, merged embeddings.
+    fp32 both sides, so only summation order differs: 2e-5 of the tensor's range."""
+    from dots_ocr_b200 import config, weights
+    from oracle.vision import VisionOracle
+    sys.path.insert(0, GOLD)
+    import make_vllm_vision_golden as G
+    d = np.load(os.path.join(GOLD, "vllm_vision_tiny.npz"))
+    cfg = config.tiny()
+    o = VisionOracle(cfg.vision, weights.make_synthetic_checkpoint(cfg, G.SEED_W, "random"), torch.float32, "cpu")
+    for name, grids in G.CASES.items():
+        pv, grid = G.case_inputs(cfg, grids)
+        assert np.array_equal(d[f"{name}_grid"], grid.numpy())
+        out, layers = o.forward(pv, grid, return_layers=True)
+        want = [d[f"{name}_patch_embed"]] + [d[f"{name}_block_{i}"] for i in range(cfg.vision.num_hidden_layers)]
+        assert len(layers) == len(want)
+        for i, (a, b) in enumerate(zip(layers, want)):
+            b = torch.from_numpy(b)
+            assert a.shape == b.shape
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()), (name, i)
+        ref = torch.from_numpy(d[f"{name}_image_embeds"])
+        assert out.shape == ref.shape and float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), name
+    # the real widths (1536, 12 heads x 128, SwiGLU 4224, 6144-wide merger), two blocks
+    wcfg = G.wide_config()
+    ow = VisionOracle(wcfg.vision, G.vision_only_checkpoint(wcfg, G.SEED_W + 1), torch.float32, "cpu")
+    pv, grid = G.case_inputs(wcfg, G.WIDE_GRIDS)
+    out, layers = ow.forward(pv, grid, return_layers=True)
+    for a, b in ((layers[-1], d["wide_block_1"]), (out, d["wide_image_embeds"])):
+        b = torch.from_numpy(b)
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
 
 
 def test_vision_pos_ids_and_rope_known_answers():
