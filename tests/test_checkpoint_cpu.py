@@ -244,3 +244,41 @@ def test_fabricated_checkpoint_directory_loads_everywhere(tmp_path):
     vc = DotsOCRConfig.from_pretrained(out)
     assert vc.vision_config.embed_dim == cfg.vision.embed_dim and vc.image_token_id == cfg.image_token_id
     assert vc.num_key_value_heads == cfg.text.num_key_value_heads and vc.architectures == ["DotsOCRForCausalLM"]
+
+
+def test_build_inputs_equals_the_hf_processor_on_a_checkpoint_directory(tmp_path):
+    """processing.build_inputs (HFTokenizer + our image path) against HF's Qwen2VLProcessor -- the class the checkpoint's
+    DotsVLProcessor extends, configured the way vLLM configures it for dots.ocr (image token <|imgpad|>,
+    vllm/model_executor/models/dots_ocr.py:149-160) -- on a fabricated directory: ids, mask, grid and pixels identical."""
+    import importlib.util
+    import numpy as np
+    from PIL import Image
+    from transformers import AutoTokenizer, Qwen2VLImageProcessor, Qwen2VLProcessor, Qwen2VLVideoProcessor
+    from dots_ocr_b200.processing import build_inputs
+    spec = importlib.util.spec_from_file_location("make_checkpoint_dir",
+                                                  os.path.join(os.path.dirname(__file__), "..", "tools", "make_checkpoint_dir.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    cfg = C.tiny()
+    out = str(tmp_path)
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(tool.hf_config_dict(cfg), f)
+    tool.write_tokenizer(cfg, out)
+    Qwen2VLImageProcessor(min_pixels=3136, max_pixels=11289600, patch_size=14, merge_size=2, temporal_patch_size=1).save_pretrained(out)
+
+    tok = AutoTokenizer.from_pretrained(out)
+    tok.image_token = "<|imgpad|>"
+    tok.padding_side = "left"
+    proc = Qwen2VLProcessor(image_processor=Qwen2VLImageProcessor.from_pretrained(out), tokenizer=tok,
+                            video_processor=Qwen2VLVideoProcessor(), chat_template=tok.chat_template)
+    proc.image_token, proc.video_token = "<|imgpad|>", "<|video_pad|>"
+    tk = HFTokenizer(out, image_token_id=cfg.image_token_id)
+    rng = np.random.default_rng(0)
+    imgs = [Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in ((90, 130), (200, 120), (57, 400))]
+    prompts = ["Parse the page", "Please output the layout: ünï 表", "x"]
+    want = proc(text=[tk.render(p) for p in prompts], images=imgs, padding=True, return_tensors="pt")
+    got = build_inputs(tk, imgs, prompts)
+    for k in ("input_ids", "attention_mask", "image_grid_thw"):
+        assert torch.equal(want[k], got[k].to(want[k].dtype)), k
+    assert torch.equal(want["pixel_values"], got["pixel_values"])
+    assert int((got["input_ids"] == cfg.image_token_id).sum()) == got["pixel_values"].shape[0] // 4
