@@ -194,11 +194,16 @@ def main(argv: Optional[list] = None) -> None:
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--weights-dir", default="./weights/DotsOCR")
     ap.add_argument("--max-batch", type=int, default=64)
+    ap.add_argument("--gpus", type=int, default=1, help="worker processes, one per GPU (cuda:0..N-1); pages go to the least-loaded")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args(argv)
-    from .batching import BatchingRunner
-    from .runner import PageRunner
-    runner = BatchingRunner(PageRunner.from_default(device=a.device, weights_dir=a.weights_dir), max_batch=a.max_batch)
+    if a.gpus > 1:
+        from .multigpu import MultiGpuRunner, b200_worker
+        runner = MultiGpuRunner(a.gpus, factory=b200_worker, factory_args=(a.weights_dir, None, a.max_batch))
+    else:
+        from .batching import BatchingRunner
+        from .runner import PageRunner
+        runner = BatchingRunner(PageRunner.from_default(device=a.device, weights_dir=a.weights_dir), max_batch=a.max_batch)
     srv = make_server(runner, a.host, a.port, a.model_name, quiet=not a.verbose)
     print(f"dots_ocr_b200 serving {a.model_name} on http://{a.host}:{srv.server_address[1]}/v1", flush=True)
     try:
@@ -207,6 +212,7 @@ def main(argv: Optional[list] = None) -> None:
         pass
     finally:
         srv.server_close()
+        runner.close()
 
 
 if __name__ == "__main__":
