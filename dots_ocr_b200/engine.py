@@ -36,6 +36,19 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _on_device(fn):
+    """Run an Engine method with the engine's GPU as the calling thread's current device.  CUDA's current device is
+    per thread and new threads start on device 0, while the C-ABI launches go to the current device's stream: a request
+    batcher or parser thread driving an engine on cuda:3 would otherwise launch on the wrong GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 def stop_list(eos_token_id) -> List[int]:
     """``eos_token_id`` as HF accepts it (None, an int, or a list of ints) -> ordered, de-duplicated list."""
     if eos_token_id is None:
@@ -158,6 +171,7 @@ class Engine:
         self.eos_check_every = 64       # decode steps between looks at the finished flags (only when a stop id is given)
 
     # ------------------------------------------------------------------------------ vision
+    @_on_device
     @torch.no_grad()
     def encode_pages_u8(self, pages, return_layers: bool = False):
         """ViT forward from uint8 RGB pages already on the device (each [H, W, 3], smart-resized: H, W multiples of 28).
@@ -178,6 +192,7 @@ class Engine:
         self.launches += len(grid)
         return self.encode_images(None, grid, return_layers=return_layers, _xin=xin)
 
+    @_on_device
     @torch.no_grad()
     def encode_images(self, pixel_values: Optional[torch.Tensor], image_grid_thw, return_layers: bool = False, _xin: Optional[torch.Tensor] = None):
         """DotsVisionTransformer.forward ([V] dots_ocr.py:580-611): pixel_values [sum S, 588] ->
@@ -370,6 +385,7 @@ class Engine:
         per_layer = 7 + (1 if pl["attn"] > 1 else 0)
         return 1 + per_layer * len(self.t_layers) + 2
 
+    @_on_device
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                  pixel_values: Optional[torch.Tensor] = None, image_grid_thw=None, max_new_tokens: int = 16,
