@@ -116,7 +116,7 @@ class BatchingRunner:
         try:
             kw = {"budgets": [b[2] for b in batch]} if self._takes_budgets else {}
             texts = self.runner.infer_batch([b[0] for b in batch], [b[1] for b in batch], max_new_tokens=n_new, **kw)
-        except BaseException as e:          # noqa: BLE001 -- the error belongs to the callers, not to the worker thread
+        except Exception as e:          # noqa: BLE001 -- the error belongs to the callers, not to the worker thread
             for b in batch:
                 b[3].set_exception(e)
             return

@@ -262,13 +262,13 @@ class ContinuousBatcher:
         for r in picked:
             try:
                 ready.append((r, b.prepare(r.image, r.prompt)))
-            except BaseException as e:      # noqa: BLE001 -- this page's caller gets the error; the others go on
+            except Exception as e:      # noqa: BLE001 -- this page's caller gets the error; the others go on
                 r.future.set_exception(e)
         if ready:
             slots = free[: len(ready)]
             try:
                 b.admit(slots, [p for _, p in ready])
-            except BaseException as e:      # noqa: BLE001
+            except Exception as e:      # noqa: BLE001
                 for r, _ in ready:
                     r.future.set_exception(e)
                 b.rearm(slots)
@@ -288,7 +288,7 @@ class ContinuousBatcher:
                 n = min(int(steps[s]), r.budget)
                 try:
                     r.future.set_result(b.decode_text(b.take(s, n)))
-                except BaseException as e:  # noqa: BLE001
+                except Exception as e:  # noqa: BLE001
                     r.future.set_exception(e)
                 del self._active[s]
                 self.stats["pages"] += 1
@@ -307,12 +307,12 @@ class ContinuousBatcher:
                 self.backend.step(self.backend.chunk)
                 self.stats["chunks"] += 1
                 self._harvest()
-            except BaseException as e:      # noqa: BLE001 -- a backend failure answers every page in flight, then the loop goes on
+            except Exception as e:      # noqa: BLE001 -- a backend failure answers every page in flight, then the loop goes on
                 for r in self._active.values():
                     if not r.future.done():
                         r.future.set_exception(e)
                 self._active.clear()
                 try:
                     self.backend.rearm(list(range(self.backend.n_slots)))
-                except BaseException:       # noqa: BLE001
+                except Exception:       # noqa: BLE001
                     pass

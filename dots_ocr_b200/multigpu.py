@@ -37,6 +37,9 @@ class _Echo:
     def infer(self, image, prompt, max_new_tokens=512):
         import time
         time.sleep(self.delay)
+        if "die" in prompt:
+            import os
+            os._exit(3)                                # a worker lost to a device fault
         if self.fail_on and self.fail_on in prompt:
             raise ValueError(f"worker {self.rank} refuses {prompt!r}")
         return f"rank{self.rank}|{getattr(image, 'size', image)}|{prompt}|{max_new_tokens}"
@@ -60,7 +63,7 @@ def _portable(exc: BaseException) -> BaseException:
 def _worker_main(rank: int, factory: Callable, factory_args: tuple, req_q, res_q) -> None:
     try:
         runner = factory(rank, *factory_args)
-    except BaseException as e:          # noqa: BLE001 -- reported to the front process, which raises it
+    except Exception as e:          # noqa: BLE001 -- reported to the front process, which raises it
         res_q.put((rank, None, False, RuntimeError(f"worker {rank} failed to start: {type(e).__name__}: {e}\n"
                                                    + traceback.format_exc(limit=5))))
         return
@@ -83,7 +86,7 @@ def _worker_main(rank: int, factory: Callable, factory_args: tuple, req_q, res_q
         req_id, image, prompt, n_new = item
         try:
             submit(image, prompt, n_new).add_done_callback(lambda f, r=req_id: done(r, f))
-        except BaseException as e:      # noqa: BLE001
+        except Exception as e:      # noqa: BLE001
             res_q.put((rank, req_id, False, _portable(e)))
     if pool is not None:
         pool.shutdown(wait=True)
@@ -108,6 +111,7 @@ class MultiGpuRunner:
         self._load = [0] * n_workers                # outstanding ViT tokens per worker
         self.served = [0] * n_workers               # pages answered per worker (observability / tests)
         self._closed = False
+        self._dead = set()                          # workers whose process has exited unexpectedly
         ready = 0
         try:
             while ready < n_workers:
@@ -128,7 +132,10 @@ class MultiGpuRunner:
         weight = max(1, page_vit_tokens(image))
         fut: Future = Future()
         with self._lock:
-            k = min(range(len(self._load)), key=lambda i: (self._load[i], i))
+            alive = [i for i in range(len(self._load)) if i not in self._dead]
+            if not alive:
+                raise RuntimeError("every GPU worker process has died")
+            k = min(alive, key=lambda i: (self._load[i], i))
             rid = next(self._ids)
             self._pending[rid] = (fut, k, weight)
             self._load[k] += weight
@@ -160,9 +167,28 @@ class MultiGpuRunner:
             if p.is_alive():
                 p.terminate()
 
+    def _reap(self) -> None:
+        """A worker process that exited while it owed answers: fail those callers instead of letting them wait forever."""
+        for k, p in enumerate(self._procs):
+            if k in self._dead or p.is_alive() or self._closed:
+                continue
+            with self._lock:
+                self._dead.add(k)
+                lost = [(rid, v[0]) for rid, v in self._pending.items() if v[1] == k]
+                for rid, _ in lost:
+                    del self._pending[rid]
+                self._load[k] = 0
+            for _, fut in lost:
+                fut.set_exception(RuntimeError(f"GPU worker {k} exited with code {p.exitcode} while serving this page"))
+
     def _collect(self) -> None:
+        import queue as _queue
         while True:
-            item = self._res.get()
+            try:
+                item = self._res.get(timeout=0.5)
+            except _queue.Empty:
+                self._reap()
+                continue
             if item is None:
                 return
             rank, rid, ok, payload = item

@@ -49,3 +49,15 @@ def test_worker_errors_reach_the_caller_and_a_dead_start_is_loud():
         r.close()
     with pytest.raises(RuntimeError, match="worker 1 failed to start"):
         MultiGpuRunner(2, factory=echo_worker, factory_args=(0.0, "", 1), start_timeout=120)
+
+
+def test_a_dead_worker_fails_its_pages_and_the_rest_go_on():
+    r = MultiGpuRunner(2, factory=echo_worker, factory_args=(0.0,), start_timeout=120)
+    try:
+        doomed = r.submit("img", "die now")                  # goes to worker 0 (both idle, lowest index)
+        with pytest.raises(RuntimeError, match="GPU worker 0 exited with code 3"):
+            doomed.result(timeout=30)
+        outs = [r.infer("img", f"p{i}") for i in range(4)]   # every later page is served by the survivor
+        assert all(o.startswith("rank1|") for o in outs)
+    finally:
+        r.close()
