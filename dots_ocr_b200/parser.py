@@ -63,8 +63,8 @@ class DotsOCRParser:
         if self._runner is None:
             from .model.inference import get_default_runner
             self._runner = get_default_runner()
-        self.model = self._runner.engine
-        self.processor = self._runner.tokenizer
+        self.model = getattr(self._runner, "engine", None)
+        self.processor = getattr(self._runner, "tokenizer", None)
 
     def _inference_with_hf(self, image, prompt):
         if self._runner is None:
@@ -202,3 +202,46 @@ class DotsOCRParser:
             for result in results:
                 w.write(json.dumps(result, ensure_ascii=False) + '\n')
         return results
+
+
+_CLI_OPTIONS = (
+    # (flag, type, default): the reference CLI's options (dots_ocr/parser.py:325-407), same names and defaults
+    ("--output", str, "./output"), ("--protocol", str, "http"), ("--ip", str, "localhost"), ("--port", int, 8000),
+    ("--model_name", str, "model"), ("--temperature", float, 0.1), ("--top_p", float, 1.0), ("--dpi", int, 200),
+    ("--max_completion_tokens", int, 16384), ("--num_thread", int, 16), ("--min_pixels", int, None), ("--max_pixels", int, None),
+)
+
+
+def main(argv=None):
+    """``python -m dots_ocr_b200.parser page.jpg [--use_hf true] ...``: the reference's command line on the B200 engine.
+    ``--use_hf`` (or a runner installed with ``set_default_runner``) serves pages in process; without it requests go to
+    ``--ip/--port`` over HTTP like the reference (``python -m dots_ocr_b200.server`` answers them)."""
+    import argparse
+    ap = argparse.ArgumentParser(description="dots.ocr document layout parser on the B200 engine")
+    ap.add_argument("input_path", type=str, help="input PDF / image file")
+    ap.add_argument("--prompt", choices=list(dict_promptmode_to_prompt), default="prompt_layout_all_en")
+    ap.add_argument("--bbox", type=int, nargs=4, metavar=("x1", "y1", "x2", "y2"), help="required by prompt_grounding_ocr")
+    for flag, typ, default in _CLI_OPTIONS:
+        ap.add_argument(flag, type=typ, default=default)
+    ap.add_argument("--no_fitz_preprocess", action="store_true", help="skip the PyMuPDF re-render of image inputs at --dpi")
+    ap.add_argument("--use_hf", type=lambda v: str(v).lower() in ("1", "true", "yes"), default=False,
+                    help="serve pages with the in-process engine instead of an HTTP endpoint")
+    a = ap.parse_args(argv)
+    fitz_preprocess = not a.no_fitz_preprocess
+    if fitz_preprocess:
+        try:
+            from .utils.doc_utils import _fitz
+            _fitz()
+        except ImportError:
+            print("PyMuPDF is not installed: image inputs are used as they are (--no_fitz_preprocess)")
+            fitz_preprocess = False
+    p = DotsOCRParser(protocol=a.protocol, ip=a.ip, port=a.port, model_name=a.model_name, temperature=a.temperature, top_p=a.top_p,
+                      max_completion_tokens=a.max_completion_tokens, num_thread=a.num_thread, dpi=a.dpi, output_dir=a.output,
+                      min_pixels=a.min_pixels, max_pixels=a.max_pixels, use_hf=a.use_hf)
+    results = p.parse_file(a.input_path, prompt_mode=a.prompt, bbox=a.bbox, fitz_preprocess=fitz_preprocess)
+    print(f"{len(results)} page(s) written under {os.path.abspath(a.output)}")
+    return results
+
+
+if __name__ == "__main__":
+    main()

@@ -272,6 +272,37 @@ def test_parser_plumbing_with_a_fake_runner(tmp_path):
         p.parse_file(str(tmp_path / "x.tiff"))
 
 
+def test_command_line_keeps_the_reference_flags(tmp_path):
+    """python -m dots_ocr_b200.parser: the reference CLI's options (dots_ocr/parser.py:325-407), pages served by the
+    process-wide runner in both modes."""
+    from PIL import Image
+    from dots_ocr_b200 import parser as P
+    from dots_ocr_b200.model import inference
+
+    class Fake:
+        def __init__(self):
+            self.seen = []
+
+        def infer(self, image, prompt, max_new_tokens=0):
+            self.seen.append((image.size, max_new_tokens))
+            return '[{"bbox": [1, 2, 30, 40], "category": "Text", "text": "hello"}]'
+    fake = Fake()
+    old = inference._state["runner"]
+    inference.set_default_runner(fake)
+    try:
+        img = tmp_path / "scan.png"
+        Image.new("RGB", (200, 100), "white").save(img)
+        res = P.main([str(img), "--output", str(tmp_path / "o1"), "--max_completion_tokens", "321", "--num_thread", "2",
+                      "--no_fitz_preprocess"])
+        assert open(res[0]["md_content_path"]).read() == "hello" and fake.seen[-1] == ((200, 100), 321)
+        res = P.main([str(img), "--output", str(tmp_path / "o2"), "--use_hf", "true", "--prompt", "prompt_ocr", "--min_pixels", "3136"])
+        assert open(res[0]["md_content_path"]).read().startswith('[{"bbox"')        # prompt_ocr: raw response is the Markdown
+        with pytest.raises(SystemExit):
+            P.main([str(img), "--prompt", "no_such_prompt"])
+    finally:
+        inference.set_default_runner(old)
+
+
 class _FakeFitz:
     """Stand-in for PyMuPDF: a "PDF" is a list of (width_pt, height_pt) page sizes; rendering scales them by the matrix."""
 
