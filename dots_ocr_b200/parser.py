@@ -214,8 +214,9 @@ _CLI_OPTIONS = (
 
 def main(argv=None):
     """``python -m dots_ocr_b200.parser page.jpg [--use_hf true] ...``: the reference's command line on the B200 engine.
-    ``--use_hf`` (or a runner installed with ``set_default_runner``) serves pages in process; without it requests go to
-    ``--ip/--port`` over HTTP like the reference (``python -m dots_ocr_b200.server`` answers them)."""
+    Pages are served in process when this process can see a GPU (or a runner was installed with ``set_default_runner``);
+    on a machine without one, and without ``--use_hf``, requests go to ``--ip/--port`` over HTTP like the reference
+    (``python -m dots_ocr_b200.server`` answers them).  See ``model/inference.py``."""
     import argparse
     ap = argparse.ArgumentParser(description="dots.ocr document layout parser on the B200 engine")
     ap.add_argument("input_path", type=str, help="input PDF / image file")

@@ -153,3 +153,36 @@ def test_unmodified_reference_client_talks_to_the_endpoint(endpoint, monkeypatch
     assert r.calls == [((64, 48), (200, 100, 50), "Parse this page", 99)]
     for k in [k for k in sys.modules if k == "dots_ocr" or k.startswith("dots_ocr.")]:
         del sys.modules[k]
+
+
+def test_the_mirror_client_uses_http_on_a_machine_without_a_gpu(endpoint, monkeypatch, capsys):
+    """dots_ocr_b200.model.inference.inference_with_vllm: no runner installed and no CUDA device here -> the reference's
+    request shape over HTTP; a dead endpoint prints the error and returns None (inference.py:46-48)."""
+    import torch
+    from dots_ocr_b200.model import inference
+    if torch.cuda.is_available():
+        monkeypatch.setenv("DOTS_B200_TRANSPORT", "http")
+    r, base = endpoint
+    port = int(base.rsplit(":", 1)[1])
+    old = inference._state["runner"]
+    inference.set_default_runner(None)
+    try:
+        img = Image.new("RGB", (48, 32), (1, 2, 3))
+        text = inference.inference_with_vllm(img, "Parse it", ip="127.0.0.1", port=port, max_completion_tokens=55, system_prompt="sys")
+        assert text == '[{"bbox": [0, 0, 48, 32], "category": "Text", "text": "sys\nPars"}]'
+        assert r.calls == [((48, 32), (1, 2, 3), "sys\nParse it", 55)]
+        srv2_port = port + 1 if port < 65000 else port - 1
+        assert inference.inference_with_vllm(img, "x", ip="127.0.0.1", port=srv2_port) is None
+        assert "request error" in capsys.readouterr().out
+        # the parser's default path goes the same way
+        from dots_ocr_b200 import DotsOCRParser
+        p = DotsOCRParser(ip="127.0.0.1", port=port, max_completion_tokens=9)
+        assert p._inference_with_vllm(img, "q").startswith('[{"bbox": [0, 0, 48, 32]') and r.calls[-1][2:] == ("q", 9)
+        # an installed runner wins over the transport arguments
+        class Local:
+            def infer(self, image, prompt, max_new_tokens=0):
+                return "local"
+        inference.set_default_runner(Local())
+        assert inference.inference_with_vllm(img, "x", ip="127.0.0.1", port=srv2_port) == "local"
+    finally:
+        inference.set_default_runner(old)
