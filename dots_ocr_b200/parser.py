@@ -8,7 +8,7 @@ rendered to Markdown by ``utils/layout_utils.py`` / ``utils/format_transformer.p
 the reference functions, JSON repair of cut-off responses included (``tests/test_postprocess.py``).  Multi-page inputs fan
 out over ``num_thread`` threads like the reference's ``parse_pdf`` (``parser.py:261-297``); the threads meet in the request
 batcher, so the pages of one document share ``generate`` calls.  PDF rasterisation needs PyMuPDF (``utils/doc_utils.py``;
-not in this image -- ``parse_pages`` takes pre-rasterised page images).  Not reproduced: drawing the layout on the page.
+not in this image -- ``parse_pages`` takes pre-rasterised page images).
 See INTEGRATION.md for patching the reference's own parser instead.
 """
 from __future__ import annotations
@@ -102,8 +102,9 @@ class DotsOCRParser:
     def _parse_single_image(self, origin_image, prompt_mode, save_dir, save_name, source="image", page_idx=0, bbox=None,
                             fitz_preprocess=False):
         """One page: prompt -> model -> layout cells in page coordinates (.json) + Markdown (.md, _nohf.md), as the reference
-        writes them (parser.py:143-253).  The page image is saved undecorated as <name>.jpg (no PyMuPDF drawing)."""
-        from .utils.layout_utils import post_process_output
+        writes them (parser.py:143-253).  <name>.jpg is the page with the layout cells drawn on it (PIL overlay instead of the
+        reference's PyMuPDF page), or the plain page when the response could not be parsed."""
+        from .utils.layout_utils import draw_layout_on_image, post_process_output
         from .utils.format_transformer import layoutjson2md
         min_pixels, max_pixels = self.min_pixels, self.max_pixels
         if prompt_mode == "prompt_grounding_ocr":
@@ -147,6 +148,10 @@ class DotsOCRParser:
             else:
                 with open(json_path, 'w', encoding='utf-8') as w:
                     json.dump(cells, w, ensure_ascii=False)
+                try:                                                    # the page with its layout drawn on it (parser.py:209-220)
+                    draw_layout_on_image(origin_rgb, cells).save(image_path)
+                except Exception as e:
+                    print(f"Error drawing layout on image: {e}")
                 if prompt_mode != 'prompt_layout_only_en' and not filtered:
                     nohf_path = os.path.join(save_dir, f"{save_name}_nohf.md")
                     write(md_path, layoutjson2md(origin_rgb, cells, text_key='text'))

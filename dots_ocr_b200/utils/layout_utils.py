@@ -73,3 +73,44 @@ def post_process_output(response, prompt_mode: str, origin_image, input_image, m
     if isinstance(repaired, list):
         repaired = "\n\n".join(cell["text"] for cell in repaired if "text" in cell)
     return repaired, True
+
+
+# ------------------------------------------------------------------ layout overlay
+# Category colours of the reference's overlay (dots_ocr/utils/layout_utils.py:14-28); anything else is drawn green.
+LAYOUT_COLORS = {
+    "Text": (0, 128, 0), "Footnote": (0, 128, 0), "Page-header": (0, 128, 0),
+    "Picture": (255, 0, 255), "Caption": (255, 165, 0), "Section-header": (0, 255, 255), "Formula": (128, 128, 128),
+    "Table": (255, 192, 203), "Title": (255, 0, 0), "List-item": (0, 0, 255), "Page-footer": (128, 0, 128),
+    "Other": (165, 42, 42), "Unknown": (0, 0, 0),
+}
+FILL_OPACITY = 0.3          # layout_utils.py:90
+LABEL_PX = 20               # label font size; the label "<reading order>_<category>" sits right of the box's top edge (:103-106)
+
+
+def draw_layout_on_image(image, cells, resized_height=None, resized_width=None, fill_bbox=True, draw_bbox=True):
+    """The page with every layout cell marked: a 30 % opaque fill (or a thin outline when ``fill_bbox`` is False) in the
+    category colour and the label ``<index>_<category>`` at the box's top-right corner -- what the reference renders through
+    a PyMuPDF page (``layout_utils.py:31-112``), done here with PIL compositing so it needs no PDF library.  Pixel-for-pixel
+    equality with PyMuPDF's rasteriser is not a goal (fonts and anti-aliasing differ); geometry, colours and opacity are the
+    reference's.  ``resized_*``: the cells are in the resized image's coordinates and are mapped back to ``image``'s."""
+    from PIL import Image, ImageDraw, ImageFont
+    base = image.convert("RGBA")
+    W, H = base.size
+    sx = (resized_width / W) if (resized_height and resized_width) else 1.0
+    sy = (resized_height / H) if (resized_height and resized_width) else 1.0
+    overlay = Image.new("RGBA", base.size, (0, 0, 0, 0))
+    draw = ImageDraw.Draw(overlay)
+    try:
+        font = ImageFont.load_default(size=LABEL_PX)
+    except TypeError:            # Pillow < 10.1: fixed-size bitmap font
+        font = ImageFont.load_default()
+    for order, cell in enumerate(cells):
+        x0, y0, x1, y1 = (int(cell["bbox"][0] / sx), int(cell["bbox"][1] / sy), int(cell["bbox"][2] / sx), int(cell["bbox"][3] / sy))
+        rgb = LAYOUT_COLORS.get(cell.get("category"), (0, 128, 0))
+        if draw_bbox and x1 >= x0 and y1 >= y0:
+            if fill_bbox:
+                draw.rectangle([x0, y0, x1, y1], fill=rgb + (int(round(255 * FILL_OPACITY)),))
+            else:
+                draw.rectangle([x0, y0, x1, y1], outline=rgb + (255,), width=1)
+        draw.text((x1, y0), f"{order}_{cell.get('category')}", fill=rgb + (255,), font=font)
+    return Image.alpha_composite(base, overlay).convert("RGB")

@@ -67,3 +67,36 @@ def test_post_process_output_failure_path():
     page, seen = Image.new("RGB", (1700, 2250)), Image.new("RGB", (1708, 2240))
     for c in G["output_fail"]:
         assert list(L.post_process_output(c["response"], "prompt_layout_all_en", page, seen)) == c["out"], c["response"][:120]
+
+
+def test_layout_overlay_geometry_colours_and_opacity():
+    """draw_layout_on_image: 30 % fill in the category colour inside the box, untouched outside, a label right of the
+    top edge, outline-only mode, and cells given in resized coordinates mapped back to the page."""
+    from PIL import Image
+    from dots_ocr_b200.utils.layout_utils import LAYOUT_COLORS, draw_layout_on_image
+    page = Image.new("RGB", (200, 100), "white")
+    cells = [{"bbox": [10, 10, 60, 40], "category": "Text"}, {"bbox": [100, 50, 150, 90], "category": "Title"},
+             {"bbox": [5, 60, 40, 95], "category": "NoSuchCategory"}]
+    out = draw_layout_on_image(page, cells)
+    assert out.size == page.size and out.mode == "RGB" and page.getpixel((30, 20)) == (255, 255, 255)      # input untouched
+
+    def blend(rgb):
+        a = round(255 * 0.3) / 255
+        return tuple(int(round(255 * (1 - a) + c * a)) for c in rgb)
+    for xy, cat in (((30, 25), "Text"), ((125, 87), "Title")):      # (125, 87): below the third cell's label
+        got, want = out.getpixel(xy), blend(LAYOUT_COLORS[cat])
+        assert all(abs(g - w) <= 1 for g, w in zip(got, want)), (cat, got, want)
+    got = out.getpixel((20, 80))
+    assert all(abs(g - w) <= 1 for g, w in zip(got, blend((0, 128, 0))))                 # unknown category: green
+    assert out.getpixel((80, 5)) == (255, 255, 255) and out.getpixel((199, 99)) == (255, 255, 255)
+    label = out.crop((61, 10, 140, 36))                                                   # "0_Text" right of the first box
+    assert any(px != (255, 255, 255) for px in label.getdata())
+
+    line = draw_layout_on_image(page, cells[:1], fill_bbox=False)
+    assert line.getpixel((10, 25)) == LAYOUT_COLORS["Text"] and line.getpixel((30, 25)) == (255, 255, 255)
+    nothing = draw_layout_on_image(page, cells[:1], draw_bbox=False)
+    assert nothing.getpixel((30, 25)) == (255, 255, 255)
+    # cells in the coordinates of a 400x200 resize of the page
+    big = draw_layout_on_image(page, [{"bbox": [20, 20, 120, 80], "category": "Table"}], resized_height=200, resized_width=400)
+    got, want = big.getpixel((30, 25)), blend(LAYOUT_COLORS["Table"])
+    assert all(abs(g - w) <= 1 for g, w in zip(got, want)) and big.getpixel((30, 60)) == (255, 255, 255)
