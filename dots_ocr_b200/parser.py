@@ -92,12 +92,8 @@ class DotsOCRParser:
     # -- pages --------------------------------------------------------------------------------
     def _fetch_image(self, origin_image, min_pixels, max_pixels):
         """RGB conversion + the resize ``fetch_image`` applies when a pixel budget is given (image_utils.py:116-138)."""
-        from .processing import to_rgb
-        image = to_rgb(origin_image)
-        if min_pixels or max_pixels:
-            rh, rw = smart_resize(image.height, image.width, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
-            image = image.resize((rw, rh))
-        return image
+        from .utils.image_utils import fetch_image
+        return fetch_image(origin_image, min_pixels=min_pixels, max_pixels=max_pixels)
 
     def _parse_single_image(self, origin_image, prompt_mode, save_dir, save_name, source="image", page_idx=0, bbox=None,
                             fitz_preprocess=False):
@@ -163,8 +159,8 @@ class DotsOCRParser:
         return result
 
     def parse_image(self, input_path, filename, prompt_mode, save_dir, bbox=None, fitz_preprocess=False):
-        from PIL import Image
-        origin_image = input_path if isinstance(input_path, Image.Image) else Image.open(input_path)
+        from .utils.image_utils import fetch_image
+        origin_image = fetch_image(input_path)          # path, file://, http(s)://, data: URL or PIL image -> RGB (parser.py:256)
         result = self._parse_single_image(origin_image, prompt_mode, save_dir, filename, source="image", bbox=bbox,
                                           fitz_preprocess=fitz_preprocess)
         result['file_path'] = input_path if isinstance(input_path, str) else filename

@@ -73,3 +73,47 @@ def PILimage_to_base64(image, format: str = "PNG") -> str:
         image.save(buf, format=format)
         payload = base64.b64encode(buf.getvalue()).decode("ascii")
     return "data:image/" + format.lower() + ";base64," + payload
+
+
+def _open_image(source):
+    """PIL image from what the reference's ``fetch_image`` accepts (``dots_ocr/utils/image_utils.py:84-111``): a PIL image,
+    an http(s) URL, a ``file://`` URL, a ``data:image...;base64,`` URL or a local path."""
+    import io
+    from PIL import Image
+    if isinstance(source, Image.Image):
+        return source
+    if not isinstance(source, str):
+        raise ValueError(f"Unrecognized image input, support local path, http url, base64 and PIL.Image, got {source!r}")
+    payload = None
+    if source.startswith(("http://", "https://")):
+        import urllib.request
+        with urllib.request.urlopen(source, timeout=60) as resp:
+            payload = resp.read()
+    elif source.startswith("data:image"):
+        import base64
+        if "base64," not in source:
+            raise ValueError("Unrecognized image input: a data: URL must carry base64 data")
+        payload = base64.b64decode(source.split("base64,", 1)[1])
+    if payload is not None:
+        img = Image.open(io.BytesIO(payload))
+        img.load()                       # decode now: the buffer does not outlive this call
+        return img
+    return Image.open(source[7:] if source.startswith("file://") else source)
+
+
+def fetch_image(image, min_pixels=None, max_pixels=None, resized_height=None, resized_width=None):
+    """Load + RGB-convert (alpha composited on white) + resize as the reference does before the model call
+    (``image_utils.py:84-138``): an explicit ``resized_height/width`` is snapped to the 28-px grid; otherwise, when a pixel
+    budget is given, the image's own size goes through ``smart_resize`` with that budget.  No budget: size unchanged."""
+    from ..processing import to_rgb
+    assert image is not None, f"image not found, maybe input format error: {image}"
+    img = to_rgb(_open_image(image))
+    target = None
+    if resized_height and resized_width:
+        target = smart_resize(resized_height, resized_width, factor=IMAGE_FACTOR)
+    elif min_pixels or max_pixels:
+        target = smart_resize(img.height, img.width, factor=IMAGE_FACTOR, min_pixels=min_pixels or MIN_PIXELS,
+                              max_pixels=max_pixels or MAX_PIXELS)
+    if target is not None:
+        img = img.resize((target[1], target[0]))
+    return img

@@ -115,6 +115,36 @@ for resp in [cases[2], cases[3], cases[4], "not json", "[]", json.dumps([{"categ
         r = L.post_process_output(resp, "prompt_layout_all_en", page, seen)
     out["output_fail"].append({"response": resp, "out": list(r)})
 
+# ---- fetch_image (dots_ocr/utils/image_utils.py:84-138): loaders, RGB conversion, the three resize rules ---------------------
+import base64          # noqa: E402
+import tempfile        # noqa: E402
+import zlib            # noqa: E402
+import numpy as np     # noqa: E402
+from dots_ocr.utils import image_utils as IU   # noqa: E402
+
+
+def fetch_inputs(tmpdir):
+    """name -> what is handed to fetch_image (shared with the test, which rebuilds the same inputs)."""
+    g = np.random.default_rng(5)
+    rgb = Image.fromarray(g.integers(0, 256, (550, 583, 3), dtype=np.uint8))
+    rgba = Image.fromarray(g.integers(0, 256, (90, 120, 4), dtype=np.uint8), "RGBA")
+    gray = Image.fromarray(g.integers(0, 256, (64, 200), dtype=np.uint8), "L")
+    png = os.path.join(tmpdir, "page.png")
+    rgb.save(png)
+    with open(png, "rb") as f:
+        data_url = "data:image/png;base64," + base64.b64encode(f.read()).decode()
+    return {"rgb": rgb, "rgba": rgba, "gray": gray, "path": png, "file_url": "file://" + png, "data_url": data_url}
+
+
+FETCH_KW = [{}, {"min_pixels": 3136, "max_pixels": 200704}, {"max_pixels": 100352}, {"min_pixels": 1003520},
+            {"resized_height": 300, "resized_width": 500}, {"resized_height": 30, "resized_width": 45, "min_pixels": 3136}]
+out["fetch"] = []
+with tempfile.TemporaryDirectory() as td:
+    for name, src in fetch_inputs(td).items():
+        for kw in FETCH_KW:
+            r = IU.fetch_image(src, **kw)
+            out["fetch"].append({"input": name, "kw": kw, "mode": r.mode, "size": list(r.size), "crc32": zlib.crc32(r.tobytes())})
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "postprocess.json")
 json.dump(out, open(path, "w"))
 print({k: len(v) for k, v in out.items()}, "->", path)

@@ -90,7 +90,7 @@ def test_layout_overlay_geometry_colours_and_opacity():
     assert all(abs(g - w) <= 1 for g, w in zip(got, blend((0, 128, 0))))                 # unknown category: green
     assert out.getpixel((80, 5)) == (255, 255, 255) and out.getpixel((199, 99)) == (255, 255, 255)
     label = out.crop((61, 10, 140, 36))                                                   # "0_Text" right of the first box
-    assert any(px != (255, 255, 255) for px in label.getdata())
+    assert any(b != 255 for b in label.tobytes())
 
     line = draw_layout_on_image(page, cells[:1], fill_bbox=False)
     assert line.getpixel((10, 25)) == LAYOUT_COLORS["Text"] and line.getpixel((30, 25)) == (255, 255, 255)
@@ -100,3 +100,36 @@ def test_layout_overlay_geometry_colours_and_opacity():
     big = draw_layout_on_image(page, [{"bbox": [20, 20, 120, 80], "category": "Table"}], resized_height=200, resized_width=400)
     got, want = big.getpixel((30, 25)), blend(LAYOUT_COLORS["Table"])
     assert all(abs(g - w) <= 1 for g, w in zip(got, want)) and big.getpixel((30, 60)) == (255, 255, 255)
+
+
+def _fetch_inputs(tmpdir):
+    """The inputs tests/golden/make_postprocess_golden.py:fetch_inputs hands to the reference's fetch_image."""
+    import base64
+    import numpy as np
+    g = np.random.default_rng(5)
+    rgb = Image.fromarray(g.integers(0, 256, (550, 583, 3), dtype=np.uint8))
+    rgba = Image.fromarray(g.integers(0, 256, (90, 120, 4), dtype=np.uint8), "RGBA")
+    gray = Image.fromarray(g.integers(0, 256, (64, 200), dtype=np.uint8), "L")
+    png = os.path.join(tmpdir, "page.png")
+    rgb.save(png)
+    with open(png, "rb") as f:
+        data_url = "data:image/png;base64," + base64.b64encode(f.read()).decode()
+    return {"rgb": rgb, "rgba": rgba, "gray": gray, "path": png, "file_url": "file://" + png, "data_url": data_url}
+
+
+def test_fetch_image_equals_the_reference_function(tmp_path):
+    """Loaders (PIL / path / file:// / data: URL), RGB conversion (alpha on white) and the three resize rules: same size,
+    mode and pixel bytes as the reference's fetch_image on every case."""
+    import zlib
+    import pytest
+    from dots_ocr_b200.utils.image_utils import fetch_image
+    inputs = _fetch_inputs(str(tmp_path))
+    assert len(G["fetch"]) == 36
+    for case in G["fetch"]:
+        r = fetch_image(inputs[case["input"]], **case["kw"])
+        assert (r.mode, list(r.size)) == (case["mode"], case["size"]), case
+        assert zlib.crc32(r.tobytes()) == case["crc32"], case
+    with pytest.raises(ValueError):
+        fetch_image(12345)
+    with pytest.raises(ValueError):
+        fetch_image("data:image/png;hex,00")
