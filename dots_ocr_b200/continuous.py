@@ -17,7 +17,7 @@ Two parts:
 * ``ContinuousBatcher`` -- the scheduler (threads, queue, slot table, budgets).  Pure host logic; tested on CPU against a
   simulated backend that enforces the row bounds (tests/test_continuous_cpu.py).
 * ``EngineSlots`` -- the backend over ``Engine``.  STATUS: written after round 1's GPU budget was spent; it has not run on
-  hardware yet (tests/test_zz_continuous_gpu.py are marked accordingly).  Nothing selects it by default.
+  hardware yet (tests/test_zzz_continuous_gpu.py are marked accordingly).  Nothing selects it by default.
 
 Row bounds the scheduler guarantees to the backend (``chunk`` = steps between harvests, ``max_new`` = largest budget):
 an occupied row is harvested at the first chunk boundary with ``step >= budget``, so ``step < budget + chunk``; idle rows are
