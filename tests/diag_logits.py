@@ -1,3 +1,5 @@
+"""Diagnostic (not collected by pytest): per-step logit error of the CUDA engine against the oracle on the tiny config.
+Lives under tests/ because it imports the oracle.  Usage: python tests/diag_logits.py [random|peaked]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
