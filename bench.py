@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--gemm-pair", dest="gemm_pair", type=int, default=None, choices=[0, 1],
                     help="CTA-pair (cta_group::2) kernel for the large prefill GEMMs (default: the library default)")
     ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
-    ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "pair", "mma"])
+    ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "mma"])
     args = ap.parse_args()
     global PAGE_HW
     PAGE_HW = (args.page, args.page)

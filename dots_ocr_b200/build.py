@@ -17,7 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdots_ocr_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["common.cu", "gemm_tcgen05.cu", "attn_fwd_mma.cu", "attn_fwd_tcgen05.cu", "attn_fwd_tcgen05_pair.cu", "attn_decode.cu", "decode_chain.cu", "elementwise.cu"]
+SOURCES = ["common.cu", "gemm_tcgen05.cu", "attn_fwd_mma.cu", "attn_fwd_tcgen05.cu", "attn_decode.cu", "elementwise.cu"]
+# documented negative results: compiled into the library only on request, never by default
+EXPERIMENTS = ["experiments/attn_fwd_tcgen05_pair.cu", "experiments/decode_chain.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -32,6 +34,9 @@ def _nvcc() -> str:
 def _digest() -> str:
     h = hashlib.sha256()
     names = sorted(os.listdir(CSRC)) + ["../../include/dots_ocr_b200.h"]
+    if os.environ.get("DOTS_BUILD_EXPERIMENTS") == "1":
+        names += ["experiments/" + n for n in sorted(os.listdir(os.path.join(CSRC, "experiments")))]
+        h.update(b"+experiments")
     for n in names:
         p = os.path.join(CSRC, n)
         if os.path.isfile(p):
@@ -50,8 +55,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
 
+    sources = SOURCES + (EXPERIMENTS if os.environ.get("DOTS_BUILD_EXPERIMENTS") == "1" else [])
+
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_DIR, os.path.basename(src).replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -62,8 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        objs = list(ex.map(compile_one, sources))
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

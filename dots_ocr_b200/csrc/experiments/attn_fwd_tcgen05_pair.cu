@@ -17,9 +17,9 @@
 //
 // STATUS: experiment.  Passes the parity tests, but measures 650 vs 1080 TFLOP/s for the single-CTA kernel: attention is bound
 // by the per-chain hand-off latency, which cluster-scope barriers lengthen, not by shared-memory bandwidth.
-#include "common.h"
-#include "ptx.cuh"
-#include "../../include/dots_ocr_b200.h"
+#include "../common.h"
+#include "../ptx.cuh"
+#include "experiments.h"
 
 namespace dots {
 

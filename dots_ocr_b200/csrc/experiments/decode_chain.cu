@@ -16,9 +16,9 @@
 // Arithmetic and rounding points are exactly those of dots_gemm_skinny_bf16 / dots_gemm_skinny_swiglu_bf16 /
 // dots_decode_residual_rmsnorm (same tiles, same k-ranges, same reduction order): results are bit-identical.
 // SURVEY.md §8a rows a20, a21, a15, a16 (decode half).
-#include "common.h"
-#include "ptx.cuh"
-#include "../../include/dots_ocr_b200.h"
+#include "../common.h"
+#include "../ptx.cuh"
+#include "experiments.h"
 
 namespace dots {
 

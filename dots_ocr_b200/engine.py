@@ -163,11 +163,6 @@ class Engine:
         self.t_inv_freq = (1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.launches = 0       # C-ABI kernel launches issued (bench.py reports it)
-        # Persistent per-layer GEMM-chain kernel for decode batches <= 64 (dots_decode_chain).  Bit-identical to the per-op
-        # path but measured SLOWER on B200 at batch 64 (2.52 vs 2.25 ms per step: its five device-wide phase barriers and
-        # exposed epilogues cost what the PDL-overlapped kernel boundaries cost, and it blocks the attention kernel's early
-        # KV prefetch) -- kept as an opt-in experiment, see DESIGN.md section 8.
-        self.decode_chain = False
         self.eos_check_every = 64       # decode steps between looks at the finished flags (only when a stop id is given)
 
     # ------------------------------------------------------------------------------ vision
@@ -307,22 +302,11 @@ class Engine:
         scale = hd ** -0.5
         ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
         n_layers = len(self.t_layers)
-        chain = self.decode_chain and st["resid"].shape[0] <= 64
-        if chain:
-            # 2 kernels per layer: attention (with the QKV finalize fused in) and the persistent GEMM-chain kernel, which also
-            # produces the next layer's QKV partials
-            ops.gemm_skinny(st["normed"], self.t_layers[0]["qkv_w"], pl["qkv"], partial=st["partial"])
         for li, L in enumerate(self.t_layers):
-            if not chain:
-                ops.gemm_skinny(st["normed"], L["qkv_w"], pl["qkv"], partial=st["partial"])
+            ops.gemm_skinny(st["normed"], L["qkv_w"], pl["qkv"], partial=st["partial"])
             ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
                                   st["ctx_len"], st["attn"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"])
             nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
-            if chain:
-                nxt_qkv = self.t_layers[li + 1]["qkv_w"] if li + 1 < n_layers else None
-                ops.decode_chain(st["attn"], L["o"], L["gu"], L["down"], nxt_qkv, st["partial"], st["resid"], st["normed"], st["act"],
-                                 L["ln2"], nxt, st["counters"], pl["o"], pl["down"], pl["qkv"], t.rms_norm_eps)
-                continue
             ops.gemm_skinny(st["attn"], L["o"], pl["o"], partial=st["partial"])
             ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed"], t.rms_norm_eps)
             ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
@@ -380,8 +364,6 @@ class Engine:
 
     def launches_per_decode_step(self, B: int) -> int:
         pl = self._decode_plan(B)
-        if self.decode_chain and B <= 64:
-            return 2 + (2 + (1 if pl["attn"] > 1 else 0)) * len(self.t_layers) + 2
         per_layer = 7 + (1 if pl["attn"] > 1 else 0)
         return 1 + per_layer * len(self.t_layers) + 2
 

@@ -119,6 +119,21 @@ def pick_splits(n_tiles: int, num_kb: int, sms: int = 148) -> int:
     return best
 
 
+def _experiment(name: str):
+    """Entry point of a kernel kept as a negative result (csrc/experiments/): present only in a library built with
+    DOTS_BUILD_EXPERIMENTS=1."""
+    lib = _lib.load()
+    if not hasattr(lib, name):
+        raise RuntimeError(f"{name} is an experiment kernel and is not in this build (DOTS_BUILD_EXPERIMENTS=1 python -m dots_ocr_b200.build --force)")
+    fn = getattr(lib, name)
+    fn.restype = C.c_int
+    return fn
+
+
+def has_experiments() -> bool:
+    return hasattr(_lib.load(), "dots_decode_chain")
+
+
 ATTN_IMPL = "tc"       # "tc": tcgen05/TMEM kernel (product path); "mma": mma.sync kernel (kept as the cross-check)
 
 
@@ -134,7 +149,7 @@ def attn_varlen(q, k, v, out, cu_seqlens, max_seqlen: int, n_q_heads: int, n_kv_
         lens = (cu_seqlens[1:] - cu_seqlens[:-1]).double()
         work = float((lens * lens).sum().item()) * 4.0 * head_dim * n_q_heads * (0.5 if causal else 1.0)
     if impl in ("tc", "pair"):
-        fn = _lib.load().dots_attn_varlen_fwd_tc if impl == "tc" else _lib.load().dots_attn_varlen_fwd_pair
+        fn = _lib.load().dots_attn_varlen_fwd_tc if impl == "tc" else _experiment("dots_attn_varlen_fwd_pair")
         with _Prof("attn_fwd_prefill" if causal else "attn_fwd_vit", work):
             rc = fn(_p(q), _ll(q.stride(0)), _p(k), _ll(k.stride(0)), _p(v), _ll(v.stride(0)),
                                                      _p(out), _ll(out.stride(0)), _p(cu_seqlens), cu_seqlens.numel() - 1,
@@ -330,7 +345,7 @@ def decode_chain(attn, w_o, w_gu, w_down, w_qkv_next, partial, resid, normed, ac
     inter = act.shape[1]
     assert counters.dtype == torch.int32 and counters.numel() >= 8 and partial.dtype == torch.float32
     qkv_n = w_qkv_next.shape[0] if w_qkv_next is not None else 0
-    rc = _lib.load().dots_decode_chain(_p(attn), _p(w_o), _p(w_gu), _p(w_down), _p(w_qkv_next), _p(partial), _p(resid), _p(normed),
+    rc = _experiment("dots_decode_chain")(_p(attn), _p(w_o), _p(w_gu), _p(w_down), _p(w_qkv_next), _p(partial), _p(resid), _p(normed),
                                        _p(act), _p(ln_mid), _p(ln_next), _p(counters), B, H, inter, qkv_n, attn.shape[1], splits_o,
                                        splits_down, splits_qkv, C.c_float(eps), _stream())
     _lib.check(rc, "dots_decode_chain")

@@ -170,24 +170,6 @@ def test_pdl_on_off_identical(tiny):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
 
 
-def test_decode_chain_kernel_on_off_identical(tiny):
-    """Decode through the persistent per-layer kernel == decode through one kernel per op (greedy ids and logits)."""
-    cfg, d = tiny
-    ck, eng = d["random"]
-    pv, grid, rows = _inputs(cfg, [(1, 8, 8), (1, 8, 8), (1, 4, 12)][:2])
-    ids = torch.stack(rows)
-    outs = []
-    try:
-        for flag in (False, True):
-            eng.decode_chain = flag
-            o = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=24, return_logits=True, use_graph=False)
-            o2 = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=24)
-            outs.append((o.sequences.cpu(), o.logits.float().cpu(), o2.sequences.cpu()))
-    finally:
-        eng.decode_chain = False
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
-
-
 def test_gpu_preprocessing_path_matches_host(tiny):
     """uint8 pages normalised / patchified on the GPU (Engine.generate(pages_u8=...)) == host processor output fed as pixel_values."""
     from dots_ocr_b200.processing import preprocess_image

@@ -407,44 +407,6 @@ def test_decode_finalize_kernels(gen):
         assert torch.equal(vc[b, :, int(pos[b])], qkv[b, (nq + nkv) * 128:].reshape(nkv, 128))
 
 
-@pytest.mark.parametrize("B,H,I,QKV,so,sd,sq", [(64, 1536, 8960, 2048, 12, 12, 8), (7, 768, 1024, 1024, 12, 16, 12), (33, 1536, 4224, 2048, 6, 11, 4),
-                                                (1, 1536, 8960, 2048, 12, 12, 8)])
-def test_decode_chain_matches_per_op_kernels(B, H, I, QKV, so, sd, sq, gen):
-    """The persistent per-layer decode kernel is bit-identical to the sequence of per-op kernels it replaces."""
-    from dots_ocr_b200.engine import _interleave_gate_up
-    ops = _ops()
-    eps = 1e-6
-    attn = _rand((B, H), gen)
-    w_o, w_down, w_qkv = _rand((H, H), gen, 0.03), _rand((H, I), gen, 0.02), _rand((QKV, H), gen, 0.03)
-    w_gu = _interleave_gate_up(_rand((I, H), gen, 0.03), _rand((I, H), gen, 0.03))
-    ln_mid, ln_next = _bf(1 + 0.1 * torch.randn(H, generator=gen, device=DEV)), _bf(1 + 0.1 * torch.randn(H, generator=gen, device=DEV))
-    resid0 = _rand((B, H), gen)
-    nmax = max(so * H, sd * H, sq * QKV) * B
-    for with_qkv in (True, False):
-        # reference: per-op kernels
-        part = torch.zeros(nmax, device=DEV, dtype=torch.float32)
-        resid, normed, act = resid0.clone(), torch.empty_like(resid0), torch.empty((B, I), device=DEV, dtype=torch.bfloat16)
-        ops.gemm_skinny(attn, w_o, so, partial=part)
-        ops.decode_residual_rmsnorm(part, so, resid, ln_mid, normed, eps)
-        ops.gemm_skinny_swiglu(normed, w_gu, act)
-        ops.gemm_skinny(act, w_down, sd, partial=part)
-        ops.decode_residual_rmsnorm(part, sd, resid, ln_next, normed, eps)
-        if with_qkv:
-            ops.gemm_skinny(normed, w_qkv, sq, partial=part)
-        # chain kernel
-        part2 = torch.zeros(nmax, device=DEV, dtype=torch.float32)
-        resid2, normed2, act2 = resid0.clone(), torch.full_like(resid0, float("nan")), torch.full((B, I), float("nan"), device=DEV, dtype=torch.bfloat16)
-        counters = torch.zeros(8, device=DEV, dtype=torch.int32)
-        ops.decode_chain(attn, w_o, w_gu, w_down, w_qkv if with_qkv else None, part2, resid2, normed2, act2, ln_mid, ln_next, counters,
-                         so, sd, sq, eps)
-        torch.cuda.synchronize()
-        assert torch.equal(act, act2)
-        assert torch.equal(resid, resid2)
-        assert torch.equal(normed, normed2)
-        if with_qkv:
-            assert torch.equal(part[: sq * B * QKV], part2[: sq * B * QKV])
-
-
 @pytest.mark.parametrize("M,N,K,epi", [(20000, 1536, 1536, "store"), (43808, 4608, 1536, "store"), (43808, 1536, 1536, "res"),
                                         (26000, 2048, 1536, "bias"), (20000, 2048, 640, "gelu"), (43808, 8448, 1536, "swiglu"),
                                         (33111, 1536, 4224, "res")])
