@@ -117,8 +117,13 @@ class BatchingRunner:
             kw = {"budgets": [b[2] for b in batch]} if self._takes_budgets else {}
             texts = self.runner.infer_batch([b[0] for b in batch], [b[1] for b in batch], max_new_tokens=n_new, **kw)
         except Exception as e:          # noqa: BLE001 -- the error belongs to the callers, not to the worker thread
+            if len(batch) == 1:
+                batch[0][3].set_exception(e)
+                return
+            # One bad page (aspect ratio above 200, unreadable image, over-long prompt ...) must not fail its up-to-63
+            # neighbours: run the pages of the failed batch one by one, so only the page that raises gets the error.
             for b in batch:
-                b[3].set_exception(e)
+                self._run([b])
             return
         for b, text in zip(batch, texts):
             b[3].set_result(text)

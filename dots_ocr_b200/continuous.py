@@ -16,8 +16,7 @@ Two parts:
 
 * ``ContinuousBatcher`` -- the scheduler (threads, queue, slot table, budgets).  Pure host logic; tested on CPU against a
   simulated backend that enforces the row bounds (tests/test_continuous_cpu.py).
-* ``EngineSlots`` -- the backend over ``Engine``.  STATUS: written after round 1's GPU budget was spent; it has not run on
-  hardware yet (tests/test_zzz_continuous_gpu.py are marked accordingly).  Nothing selects it by default.
+* ``EngineSlots`` -- the backend over ``Engine`` (GPU cases: tests/test_zzz_continuous_gpu.py).
 
 Row bounds the scheduler guarantees to the backend (``chunk`` = steps between harvests, ``max_new`` = largest budget):
 an occupied row is harvested at the first chunk boundary with ``step >= budget``, so ``step < budget + chunk``; idle rows are
@@ -53,12 +52,12 @@ class EngineSlots:
         self.ctx_max = _round_up(self.max_prompt + self.max_new + self.chunk, 64)
         dev = engine.device
         stops = list(getattr(tokenizer, "stop_ids", ())) or ([] if tokenizer.eos_token_id is None else [tokenizer.eos_token_id])
-        self.eos = stops[0] if stops else None            # the kernels stop rows on the primary id; others are cut on the host
+        self.stops = [int(x) for x in stops]              # any of these finishes a row on the device (dots_argmax_advance)
         self.pad = int(tokenizer.pad_token_id)
         with torch.no_grad(), torch.cuda.device(dev):
             kc, vc = engine._alloc_cache(self.n_slots, self.ctx_max)
             lens = torch.ones(self.n_slots, dtype=torch.int64, device=dev)
-            self.st = engine._new_decode_state(self.n_slots, lens, kc, vc, self.ctx_max, self.n_cols, self.eos, self.pad)
+            self.st = engine._new_decode_state(self.n_slots, lens, kc, vc, self.ctx_max, self.n_cols, self.stops, self.pad)
         self.rearm(list(range(self.n_slots)))
         self._graph = None
         self._warm = False
@@ -107,7 +106,7 @@ class EngineSlots:
             pos = (lens - 1).to(torch.int32)
             ctx = lens.to(torch.int32)
             fin = torch.zeros(n, dtype=torch.int32, device=dev)
-            ops.argmax_advance(logits, last, out, step, pos, ctx, fin, -1 if self.eos is None else self.eos, self.pad, None)
+            ops.argmax_advance(logits, last, out, step, pos, ctx, fin, tuple(self.stops[: ops.MAX_STOP_IDS]), self.pad, None)
             eng.launches += 5
             idx = torch.tensor(list(slots), dtype=torch.int64, device=dev)
             st["last"].index_copy_(0, idx, last)
@@ -133,15 +132,7 @@ class EngineSlots:
                 cap = torch.cuda.Stream(device=eng.device)
                 cap.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(cap):
-                    try:
-                        g = ops.Graph()
-                        with g:
-                            eng._decode_step(st)
-                    except RuntimeError:
-                        ops.set_pdl(False)               # a driver that cannot capture programmatic-dependent-launch edges
-                        g = ops.Graph()
-                        with g:
-                            eng._decode_step(st)
+                    g = ops.capture(lambda: eng._decode_step(st))
                 torch.cuda.current_stream().wait_stream(cap)
                 self._graph = g
             for _ in range(k - done):

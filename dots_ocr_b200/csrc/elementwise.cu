@@ -360,12 +360,15 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long lds, 
 // ------------------------------------------------------------------ greedy argmax + sequence state advance
 // logits bf16 -> fp32 -> argmax, lowest index wins ties (torch.argmax; generation/utils.py:2762,2793).
 // Then the HF bookkeeping of one greedy step: finished rows emit pad, EOS marks a row finished
-// (utils.py:2796-2805), the token is appended, position / context length advance.
+// (utils.py:2796-2805; any id of generation_config.eos_token_id stops a row), the token is appended, position / context
+// length advance.
+struct StopIds { long long id[DOTS_MAX_STOP_IDS]; int n; };
+
 __global__ void __launch_bounds__(1024) argmax_advance_kernel(const bf16* __restrict__ logits, long long ldl, int V,
                                                               long long* __restrict__ next_ids, long long* __restrict__ out_ids,
                                                               long long out_ld, int* __restrict__ step, int* __restrict__ pos,
                                                               int* __restrict__ ctx_len, int* __restrict__ finished,
-                                                              long long eos_id, long long pad_id, const long long* __restrict__ forced,
+                                                              const StopIds stops, long long pad_id, const long long* __restrict__ forced,
                                                               long long forced_ld) {
     pdl_wait();
     pdl_launch_dependents();
@@ -407,7 +410,12 @@ __global__ void __launch_bounds__(1024) argmax_advance_kernel(const bf16* __rest
             if (forced) tok = forced[(long long)b * forced_ld + st];   // teacher forcing (parity tests)
             if (finished) {
                 if (finished[b]) tok = pad_id;
-                else if (eos_id >= 0 && tok == eos_id) finished[b] = 1;
+                else {
+                    bool hit = false;
+#pragma unroll
+                    for (int i = 0; i < DOTS_MAX_STOP_IDS; ++i) hit |= (i < stops.n) && (tok == stops.id[i]);
+                    if (hit) finished[b] = 1;
+                }
             }
             next_ids[b] = tok;
             if (out_ids) out_ids[(long long)b * out_ld + st] = tok;
@@ -680,10 +688,15 @@ extern "C" int dots_gather_rows(const void* src, long long lds, const int* rows,
 }
 
 extern "C" int dots_argmax_advance(const void* logits, long long ldl, int batch, int vocab, long long* next_ids, long long* out_ids,
-                                   long long out_ld, int* step, int* pos, int* ctx_len, int* finished, long long eos_id,
-                                   long long pad_id, const long long* forced_ids, long long forced_ld, void* stream) {
+                                   long long out_ld, int* step, int* pos, int* ctx_len, int* finished, const long long* stop_ids,
+                                   int n_stops, long long pad_id, const long long* forced_ids, long long forced_ld, void* stream) {
     DOTS_REQUIRE(batch > 0 && vocab % 8 == 0 && ldl % 8 == 0, "dots_argmax_advance: vocab and pitch must be multiples of 8");
-    DOTS_CHECK_CUDA(launch_ex(argmax_advance_kernel, dim3(batch), dim3(1024), (size_t)(0), ST(stream), true, (const bf16*)logits, ldl, vocab, next_ids, out_ids, out_ld, step, pos, ctx_len, finished, eos_id, pad_id, forced_ids, forced_ld));
+    DOTS_REQUIRE(n_stops >= 0 && n_stops <= DOTS_MAX_STOP_IDS && (n_stops == 0 || stop_ids), "dots_argmax_advance: at most %d stop ids (got %d)",
+                 DOTS_MAX_STOP_IDS, n_stops);
+    StopIds stops{};
+    stops.n = n_stops;
+    for (int i = 0; i < n_stops; ++i) stops.id[i] = stop_ids[i];
+    DOTS_CHECK_CUDA(launch_ex(argmax_advance_kernel, dim3(batch), dim3(1024), (size_t)(0), ST(stream), true, (const bf16*)logits, ldl, vocab, next_ids, out_ids, out_ld, step, pos, ctx_len, finished, stops, pad_id, forced_ids, forced_ld));
     return 0;
 }
 

@@ -63,8 +63,8 @@ def stop_list(eos_token_id) -> List[int]:
 def finalize_new_tokens(out_new: torch.Tensor, stops: List[int], pad: int) -> torch.Tensor:
     """The generated block [B, N] the way HF's greedy loop leaves it: everything after a row's first stop id is
     ``pad``, and the block ends at the step where the last row stopped (``GenerationMixin._sample``: finished rows
-    keep emitting pad, the loop ends once every row has finished).  The decode kernels pad after the PRIMARY stop id
-    (``stops[0]``) on the device; secondary ids are handled here."""
+    keep emitting pad, the loop ends once every row has finished).  The decode kernels already stop a row on any of the
+    first ``ops.MAX_STOP_IDS`` ids and pad behind it on the device; this pass is what makes longer lists correct too."""
     if not stops:
         return out_new
     hit = out_new == stops[0]
@@ -314,7 +314,7 @@ class Engine:
             ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed"], t.rms_norm_eps)
         ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
         ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
-                           st["eos"], st["pad"], st["forced"])
+                           st["stops"], st["pad"], st["forced"])
 
     def _new_decode_state(self, B: int, lens: torch.Tensor, kc, vc, ctx_max: int, N: int, eos_token_id=None, pad_token_id: int = 0,
                           forced_ids: Optional[torch.Tensor] = None) -> dict:
@@ -323,7 +323,7 @@ class Engine:
         dev = self.device
         H = t.hidden_size
         stops = stop_list(eos_token_id)
-        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, eos=stops[0] if stops else -1, pad=int(pad_token_id))
+        st = dict(plan=self._decode_plan(B), kc=kc, vc=vc, ctx_max=ctx_max, stops=tuple(stops[: ops.MAX_STOP_IDS]), pad=int(pad_token_id))
         pl = st["plan"]
         max_part = max(pl["qkv"] * (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim, pl["o"] * H, pl["down"] * H)
         st["partial"] = torch.empty(max_part * B, device=dev, dtype=torch.float32)
@@ -420,7 +420,7 @@ class Engine:
         ops.rmsnorm(hl, self.final_norm, t.rms_norm_eps, out=st["normed"])
         ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
         ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
-                           st["eos"], st["pad"], st["forced"])
+                           st["stops"], st["pad"], st["forced"])
         self.launches += 4
         del x
         if return_logits:
@@ -429,7 +429,7 @@ class Engine:
         n_steps = N - 1
         per_step = self.launches_per_decode_step(B)
         # with a stop id, look at the finished flags every `eos_check_every` steps and leave once every page is done
-        check = int(self.eos_check_every) if st["eos"] >= 0 else 0
+        check = int(self.eos_check_every) if st["stops"] else 0
 
         def all_finished() -> bool:
             return bool(st["finished"].all().item())
@@ -446,16 +446,7 @@ class Engine:
                     cap = torch.cuda.Stream(device=dev)
                     cap.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(cap):
-                        try:
-                            g = ops.Graph()
-                            with g:
-                                self._decode_step(st)
-                        except RuntimeError:
-                            # a driver that cannot capture programmatic-dependent-launch edges: plain stream order
-                            ops.set_pdl(False)
-                            g = ops.Graph()
-                            with g:
-                                self._decode_step(st)
+                        g = ops.capture(lambda: self._decode_step(st))
                         # capture does not execute: replay for every remaining step
                         done += replay_steps(g.launch, n_steps - 1, check, all_finished)
                     torch.cuda.current_stream().wait_stream(cap)

@@ -183,11 +183,17 @@ class MultiGpuRunner:
 
     def _collect(self) -> None:
         import queue as _queue
+        import time as _time
+        last_reap = _time.monotonic()
         while True:
+            # look for dead workers every 0.5 s whether or not results keep arriving (a steady stream from the survivors must
+            # not hide a worker that died owing answers)
+            if _time.monotonic() - last_reap >= 0.5:
+                self._reap()
+                last_reap = _time.monotonic()
             try:
                 item = self._res.get(timeout=0.5)
             except _queue.Empty:
-                self._reap()
                 continue
             if item is None:
                 return

@@ -14,6 +14,8 @@ K = _lib.header_constants()
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_SWIGLU = (
     K["DOTS_EPI_STORE"], K["DOTS_EPI_BIAS"], K["DOTS_EPI_BIAS_GELU"], K["DOTS_EPI_RESIDUAL"], K["DOTS_EPI_SWIGLU"])
 
+MAX_STOP_IDS = K["DOTS_MAX_STOP_IDS"]
+
 _ll = C.c_longlong
 _vp = C.c_void_p
 
@@ -300,13 +302,20 @@ def gather_rows(src, rows, out=None):
     return out
 
 
-def argmax_advance(logits, next_ids, out_ids=None, step=None, pos=None, ctx_len=None, finished=None, eos_id: int = -1,
+def argmax_advance(logits, next_ids, out_ids=None, step=None, pos=None, ctx_len=None, finished=None, stop_ids=(),
                    pad_id: int = 0, forced_ids=None):
+    """``stop_ids``: an int (< 0 = none) or a sequence of up to DOTS_MAX_STOP_IDS ids; any of them finishes a row."""
     _bf16_2d(logits, "logits")
     B, V = logits.shape
+    if isinstance(stop_ids, int):
+        stop_ids = () if stop_ids < 0 else (stop_ids,)
+    stops = [int(s) for s in stop_ids]
+    if len(stops) > K["DOTS_MAX_STOP_IDS"]:
+        raise ValueError(f"at most {K['DOTS_MAX_STOP_IDS']} stop ids are handled on the device, got {len(stops)}")
+    arr = (_ll * max(1, len(stops)))(*stops)
     rc = _lib.load().dots_argmax_advance(_p(logits), _ll(logits.stride(0)), B, V, _p(next_ids), _p(out_ids),
                                          _ll(out_ids.stride(0) if out_ids is not None else 0), _p(step), _p(pos), _p(ctx_len),
-                                         _p(finished), _ll(eos_id), _ll(pad_id), _p(forced_ids),
+                                         _p(finished), arr, len(stops), _ll(pad_id), _p(forced_ids),
                                          _ll(forced_ids.stride(0) if forced_ids is not None else 0), _stream())
     _lib.check(rc, "dots_argmax_advance")
 
@@ -388,3 +397,25 @@ class Graph:
                 _lib.load().dots_graph_destroy(self.exec)
         except Exception:
             pass
+
+
+def capture(fn) -> Graph:
+    """Capture ``fn()`` (C-ABI launches on the current stream) into a replayable graph.  A driver that cannot record
+    programmatic-dependent-launch edges fails the capture with a stream-capture error: only then is PDL switched off
+    (for the process, with a warning) and the capture retried; any other failure propagates unchanged."""
+    try:
+        g = Graph()
+        with g:
+            fn()
+        return g
+    except RuntimeError as e:
+        msg = str(e).lower()
+        if not any(k in msg for k in ("capture", "not permitted", "not supported", "unsupported")):
+            raise
+        import warnings
+        warnings.warn(f"CUDA graph capture with programmatic dependent launch failed ({e}); retrying with PDL off")
+        set_pdl(False)
+        g = Graph()
+        with g:
+            fn()
+        return g

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 1
+#define DOTS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DOTS_API __attribute__((visibility("default")))
@@ -156,13 +156,16 @@ DOTS_API int dots_gather_rows(const void* src, long long lds, const int* rows, v
                      void* stream);
 
 /* Greedy step: argmax over bf16 logits in fp32, lowest index wins ties ([G]:2762,2793); finished rows emit
- * pad, EOS marks finished ([G]:2796-2805); appends to out_ids[b, step[b]] and advances step/pos/ctx_len.
- * forced_ids (optional) overrides the chosen token (teacher forcing for parity tests).  Nullable: out_ids,
- * step, pos, ctx_len, finished, forced_ids.  eos_id < 0 disables EOS. */
+ * pad, ANY of the stop ids marks a row finished ([G]:2796-2805 with generation_config.eos_token_id a list);
+ * appends to out_ids[b, step[b]] and advances step/pos/ctx_len.  stop_ids is a HOST pointer to n_stops <=
+ * DOTS_MAX_STOP_IDS ids (copied into the launch; n_stops == 0 disables stopping).  forced_ids (optional)
+ * overrides the chosen token (teacher forcing for parity tests).  Nullable: out_ids, step, pos, ctx_len,
+ * finished, forced_ids. */
+#define DOTS_MAX_STOP_IDS 4
 DOTS_API int dots_argmax_advance(const void* logits, long long ldl, int batch, int vocab, long long* next_ids,
                         long long* out_ids, long long out_ld, int* step, int* pos, int* ctx_len, int* finished,
-                        long long eos_id, long long pad_id, const long long* forced_ids, long long forced_ld,
-                        void* stream);
+                        const long long* stop_ids, int n_stops, long long pad_id, const long long* forced_ids,
+                        long long forced_ld, void* stream);
 
 /* ---- decode-step fused finalize kernels (split-K reduce + HF rounding points) ------------------ */
 DOTS_API int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,

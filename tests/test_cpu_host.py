@@ -580,3 +580,44 @@ def test_replay_steps_checks_every_k_and_stops_early():
     assert replay_steps(lambda: log.append("L"), 8, 4, finished) == 8       # no question after the last launch
     assert log.count("C") == 1
     assert replay_steps(lambda: None, 0, 4, lambda: True) == 0
+
+
+def test_one_bad_page_does_not_fail_its_batch():
+    """a page whose preprocessing raises must fail only its own caller, not the up-to-63 other pages that
+    happened to share its batch."""
+    from dots_ocr_b200.batching import BatchingRunner
+
+    class Fake:
+        def __init__(self):
+            self.calls = []
+
+        def infer_batch(self, images, prompts, max_new_tokens=512):
+            self.calls.append(len(images))
+            if any(im == "bad" for im in images):
+                raise ValueError("absolute aspect ratio must be smaller than 200")
+            return [f"{im}:{pr}" for im, pr in zip(images, prompts)]
+
+    fake = Fake()
+    br = BatchingRunner(fake, max_batch=8, max_wait_ms=300)
+    futs = [br.submit(im, f"p{i}", 16) for i, im in enumerate(["a", "b", "bad", "c"])]
+    br.close(10)
+    assert [f.result(5) for i, f in enumerate(futs) if i != 2] == ["a:p0", "b:p1", "c:p3"]
+    with pytest.raises(ValueError, match="aspect ratio"):
+        futs[2].result(5)
+    assert fake.calls[0] == 4 and sorted(fake.calls[1:]) == [1, 1, 1, 1]       # the batch, then each page on its own
+
+
+def test_grounding_prompt_bbox_uses_the_reference_rounding():
+    """parser.get_prompt scales the grounding bbox with pre_process_bboxes (int(x / (origin_w / w))), as the reference does
+    (dots_ocr/parser.py:135-139); x=85, origin width 204, model width 1092 is a case where int(x * (w / origin_w)) is off by one."""
+    from PIL import Image
+    from dots_ocr_b200.parser import DotsOCRParser
+    from dots_ocr_b200.utils.layout_utils import pre_process_bboxes
+    from dots_ocr_b200.utils.prompts import dict_promptmode_to_prompt
+    origin = Image.new("RGB", (204, 204))
+    image = Image.new("RGB", (1092, 1092))
+    p = DotsOCRParser.__new__(DotsOCRParser)
+    got = p.get_prompt("prompt_grounding_ocr", bbox=[85, 85, 120, 130], origin_image=origin, image=image, min_pixels=3136, max_pixels=11289600)
+    want = pre_process_bboxes(origin, [[85, 85, 120, 130]], input_width=1092, input_height=1092, min_pixels=3136, max_pixels=11289600)[0]
+    assert got == dict_promptmode_to_prompt["prompt_grounding_ocr"] + str(want)
+    assert want[0] == 455 and int(85 * (1092 / 204)) == 454

@@ -343,11 +343,13 @@ def test_argmax_advance(gen):
     fin = torch.zeros(B, device=DEV, dtype=torch.int32)
     fin[4] = 1
     eos = int(logits[3].float().argmax())
-    ops.argmax_advance(logits, nxt, out_ids, step, pos, ctx, fin, eos_id=eos, pad_id=11)
+    ops.argmax_advance(logits, nxt, out_ids, step, pos, ctx, fin, stop_ids=(eos, 151935), pad_id=11)      # two stop ids: rows 2 and 3 stop
     ref = logits.float().argmax(-1)
     assert nxt[0] == ref[0] and nxt[1] == 777 and nxt[2] == 151935 and nxt[3] == eos and nxt[4] == 11
-    assert fin.tolist() == [0, 0, 0, 1, 1]
+    assert fin.tolist() == [0, 0, 1, 1, 1]
     assert torch.equal(out_ids[:, 0], nxt) and step.tolist() == [1] * B
+    with pytest.raises(ValueError):
+        ops.argmax_advance(logits, nxt, out_ids, step, pos, ctx, fin, stop_ids=tuple(range(ops.MAX_STOP_IDS + 1)), pad_id=11)
     assert pos.tolist() == [1, 2, 3, 4, 5] and ctx.tolist() == [2, 3, 4, 5, 6]
 
 

@@ -77,7 +77,27 @@ def test_both_rows_stop_early_and_the_loop_leaves(peaked):
     assert used < 30 * eng.launches_per_decode_step(2)          # ~17 steps, not 199
 
 
-def test_secondary_stop_id_pads_on_the_host(peaked):
+def test_secondary_stop_id_finishes_the_row_on_the_device(peaked):
+    """generation_config.eos_token_id is a list and the model ends its turn with the SECOND id: the row's finished flag must
+    still go up on the device, so the early exit fires and a continuous-batching slot is released."""
+    cfg, eng = peaked
+    ids = torch.tensor([[5, 6, 7, 8], [5, 6, 7, 8]])
+    c = _chain(cfg, 8, 13)
+    primary_never = cfg.text.vocab_size - 3
+    assert primary_never not in c
+    old = eng.eos_check_every
+    try:
+        eng.eos_check_every = 8
+        l0 = eng.launches
+        out = eng.generate(ids, max_new_tokens=200, eos_token_id=[primary_never, c[12]], pad_token_id=0).sequences
+        used = eng.launches - l0
+    finally:
+        eng.eos_check_every = old
+    assert out.shape == (2, 4 + 13) and out[0, 4:].tolist() == c
+    assert used < 30 * eng.launches_per_decode_step(2)          # left after ~16 steps, not 199
+
+
+def test_two_stop_ids_each_row_its_own(peaked):
     cfg, eng = peaked
     ids = torch.tensor([[5, 6, 7, 8], [9, 10, 11, 12]])
     N = 24

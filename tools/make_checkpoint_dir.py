@@ -110,7 +110,7 @@ def write_dir(cfg, out: str, seed: int = 0, flavour: str = "random", shards: int
     with open(os.path.join(out, "config.json"), "w") as f:
         json.dump(hf_config_dict(cfg), f, indent=2)
     with open(os.path.join(out, "generation_config.json"), "w") as f:
-        json.dump({"do_sample": False, "eos_token_id": [sp["<|endofassistant|>"], sp["<|endoftext|>"]],
+        json.dump({"do_sample": False, "eos_token_id": [sp["<|endoftext|>"], sp["<|endofassistant|>"]],
                    "pad_token_id": sp["<|endoftext|>"], "max_new_tokens": 24000}, f, indent=2)
     write_tokenizer(cfg, out)
     from transformers import Qwen2VLImageProcessor
