@@ -228,7 +228,7 @@ def test_fabricated_checkpoint_directory_loads_everywhere(tmp_path):
     assert tk.encode_chat(prompt, 9) == st.encode_chat(prompt, 9)
     assert tk.decode(list(prompt.encode())) == prompt == st.decode(list(prompt.encode()))
     sp = info["special_tokens"]
-    assert tk.stop_ids == (sp["<|endofassistant|>"], sp["<|endoftext|>"]) and tk.pad_token_id == sp["<|endoftext|>"]
+    assert tk.stop_ids == (sp["<|endoftext|>"], sp["<|endofassistant|>"]) and tk.pad_token_id == sp["<|endoftext|>"]
     with open(os.path.join(out, "model.safetensors.index.json")) as f:
         index = json.load(f)
     assert set(index["weight_map"]) == set(want) and set(index["weight_map"].values()) == \
