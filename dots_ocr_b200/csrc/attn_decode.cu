@@ -27,7 +27,10 @@ constexpr int DEC_THREADS = (DEC_WARPS + 1) * 32;                          // + 
 constexpr int DEC_RING_KEYS = DEC_TILE * DEC_WARPS;                        // 64 keys per ring tile
 constexpr int DEC_BOX_BYTES = DEC_RING_KEYS * 128;                         // [64 keys][64 dims] bf16 = 8 KB (one swizzle box)
 constexpr int DEC_STAGE_BYTES = 4 * DEC_BOX_BYTES;                         // K lo | K hi | V lo | V hi = 32 KB
-constexpr int DEC_STAGES = 3;
+#ifndef DEC_STAGES_OVR
+#define DEC_STAGES_OVR 3
+#endif
+constexpr int DEC_STAGES = DEC_STAGES_OVR;
 constexpr int DEC_SMEM = 1024 /*align*/ + 4096 /*Q*/ + DEC_STAGES * DEC_STAGE_BYTES + 256 /*barriers*/;
 
 struct DecParams {

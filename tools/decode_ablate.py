@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ctx", type=int, default=1881)
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="override the flash-decoding split count of the plan")
+    ap.add_argument("--quick", action="store_true", help="only the full step and the attention ablation")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = config.full()
@@ -35,6 +37,10 @@ def main():
 
     real = {n: getattr(ops, n) for n in ("gemm_skinny", "gemm_skinny_swiglu", "attn_decode_fused", "decode_residual_rmsnorm",
                                          "decode_embed_rmsnorm", "argmax_advance")}
+
+    if args.attn_splits:
+        plan0 = eng._decode_plan
+        eng._decode_plan = lambda b: dict(plan0(b), attn=args.attn_splits)
 
     def run(stub=(), which_skinny=None):
         st = eng._new_decode_state(B, lens, kc, vc, ctx_max, args.steps + 2)
@@ -78,7 +84,8 @@ def main():
     qkv_n = (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim
     full = run()
     res = {"full_ms": round(full, 4)}
-    for name, stub, shape in [("attention(+qkv finalize)", ("attn_decode_fused",), None),
+    cases = [("attention(+qkv finalize)", ("attn_decode_fused",), None)] if args.quick else None
+    for name, stub, shape in cases or [("attention(+qkv finalize)", ("attn_decode_fused",), None),
                               ("qkv gemm", ("gemm_skinny",), (qkv_n, H)), ("o gemm", ("gemm_skinny",), (H, H)),
                               ("down gemm", ("gemm_skinny",), (H, I)), ("lm_head gemm", ("gemm_skinny",), (t.vocab_size, H)),
                               ("gate|up gemm + swiglu", ("gemm_skinny_swiglu",), None),
