@@ -132,97 +132,65 @@ def usable_cpu_threads() -> int:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference(new_tokens: int, threads: int, decode_steps: int = 8):
-    """The reference's HF CPU float32 path (oracle port: restated ViT + HF Qwen2ForCausalLM) on the host
-    cores, on a BOUNDED sample of the same workload: one 1024x1024 page through 2 of 42 ViT blocks and 2
-    of 28 decoder layers at full width (plus patch-embed, merger, lm_head), `decode_steps` greedy steps;
-    per-layer times are then scaled by the real layer counts."""
+def cpu_reference(new_tokens: int, threads: int, ck=None, cfg=None):
+    """The reference's HF CPU float32 path (oracle port: restated ViT + HF Qwen2ForCausalLM.generate, greedy) on the host
+    cores: ONE page of the benchmark workload at FULL depth (42 ViT blocks, 28 decoder layers, `new_tokens` greedy steps with
+    a KV cache), timed directly from pixel_values to the last token -- no per-layer extrapolation.  About a minute on 16
+    threads.  `ck`: an already generated bf16 checkpoint (any device) to convert, else the seeded synthetic one is drawn here."""
     import torch
     from dots_ocr_b200 import config, weights
     from oracle.model import DotsOracle
     torch.set_num_threads(threads)
-    full, small = config.full(), config.small()
+    full = cfg or config.full()
     s_vit, t_img = _page_tokens(full)
-    ck = weights.make_synthetic_checkpoint(small, 0, "random", device="cpu")
-    orc = DotsOracle(small, ck, torch.float32, "cpu")
+    t0 = time.perf_counter()
+    if ck is None:
+        ck = weights.make_synthetic_checkpoint(full, 0, "random", device="cpu")
+    else:
+        ck = {k: v.to("cpu") for k, v in ck.items()}
+    orc = DotsOracle(full, ck, torch.float32, "cpu")
     del ck
+    t_build = time.perf_counter() - t0
     g = torch.Generator().manual_seed(1234)
     pv = torch.randn(s_vit, full.vision.patch_dim, generator=g)
-    grid = torch.tensor([[1, PAGE_HW[0] * 1036 // 1024 // 14, PAGE_HW[1] * 1036 // 1024 // 14]])
     from dots_ocr_b200.utils.image_utils import vit_grid
     gh, gw = vit_grid(*PAGE_HW)
     grid = torch.tensor([[1, gh, gw]])
     ids = _prompt_ids(full, 1, t_img)
-    v = orc.vision
-
-    def clock(fn):
-        t0 = time.perf_counter(); r = fn(); return r, time.perf_counter() - t0
-
     with torch.no_grad():
-        # ViT: fixed part (patch embed + post norm + merger) and per-block part
-        from oracle.vision import rot_pos_emb, rms_norm
-        ang = rot_pos_emb(grid.tolist(), 2, full.vision.head_dim, full.vision.rope_theta, "cpu")
-        cos, sin = ang.cos(), ang.sin()
-        x, t_pe = clock(lambda: v.patch_embed(pv))
-        cu = [0, s_vit]
-        x, t_b0 = clock(lambda: v.block(0, x, cu, cos, sin))
-        x, t_b1 = clock(lambda: v.block(1, x, cu, cos, sin))
-        img, t_mg = clock(lambda: v.merger(rms_norm(x, v.w["post_trunk_norm.weight"], full.vision.rms_norm_eps)))
-        t_vit_layer = min(t_b0, t_b1)
-        t_vit = t_pe + t_mg + full.vision.num_hidden_layers * t_vit_layer
-        # prefill: embeddings -> 2 layers -> head; per-layer time from the 2-layer model
-        emb = orc.llm.model.embed_tokens(ids)
-        emb = emb.masked_scatter((ids == full.image_token_id).unsqueeze(-1).expand_as(emb), img.to(emb.dtype))
-        from transformers import DynamicCache
-        cache = DynamicCache(config=orc.llm.config)
-        out, t_pf2 = clock(lambda: orc.llm(inputs_embeds=emb, past_key_values=cache, use_cache=True, logits_to_keep=1))
-        _, t_head = clock(lambda: orc.llm.lm_head(out.logits.new_zeros(1, 1, full.text.hidden_size)))
-        t_prefill_layer = max(1e-9, (t_pf2 - t_head) / 2)
-        t_prefill = full.text.num_hidden_layers * t_prefill_layer + t_head
-        # decode steps on the 2-layer model with a KV cache.  One-token steps are tiny memory-bound ops: a very wide thread
-        # pool can be slower than a moderate one, so the reference gets the better of {all usable threads, 16 threads}.
-        nxt = out.logits[:, -1].argmax(-1, keepdim=True)
-        best = None
-        for nthr in sorted({threads, min(threads, 16)}, reverse=True):
-            torch.set_num_threads(nthr)
-            ts = []
-            for _ in range(decode_steps):
-                o, dt = clock(lambda: orc.llm(input_ids=nxt, past_key_values=cache, use_cache=True))
-                nxt = o.logits[:, -1].argmax(-1, keepdim=True)
-                ts.append(dt)
-            ts.sort()
-            med = ts[len(ts) // 2]
-            if best is None or med < best[0]:
-                best = (med, nthr)
-        torch.set_num_threads(threads)
-        t_step2, decode_threads = best
-        _, t_head1 = clock(lambda: orc.llm.lm_head(out.logits.new_zeros(1, 1, full.text.hidden_size)))
-        t_dec_layer = max(1e-9, (t_step2 - min(t_head, t_head1)) / 2)
-        t_step = full.text.num_hidden_layers * t_dec_layer + min(t_head, t_head1)
-    total = t_vit + t_prefill + new_tokens * t_step
-    return dict(pages_per_sec=1.0 / total, t_vit=t_vit, t_prefill=t_prefill, t_step=t_step,
-                sample=(f"1 page {PAGE_HW[0]}x{PAGE_HW[1]}: 2/42 ViT blocks + 2/28 decoder layers at full width (fp32, "
-                        f"{threads} threads; decode steps with {decode_threads}), {decode_steps} decode steps; per-layer times scaled to 42/28 layers, "
-                        f"N={new_tokens} new tokens"))
+        # warm-up: thread pool, allocator and code paths, on a sliver of the work (one 8x8-patch image, 4 tokens)
+        wpv = torch.randn(64, full.vision.patch_dim, generator=g)
+        wids = torch.cat([ids[0, :4], torch.full((16,), full.image_token_id), ids[0, -4:]]).unsqueeze(0)
+        orc.generate(wids, pixel_values=wpv, image_grid_thw=torch.tensor([[1, 8, 8]]), max_new_tokens=4)
+        t0 = time.perf_counter()
+        emb = orc.inputs_embeds(ids, pv, grid)                                   # ViT (42 blocks) + embed + masked_scatter
+        t_vit = time.perf_counter() - t0
+        out = orc.llm.generate(inputs_embeds=emb, attention_mask=torch.ones_like(ids), max_new_tokens=new_tokens, min_new_tokens=new_tokens,
+                               do_sample=False, pad_token_id=0)
+        total = time.perf_counter() - t0
+    assert out.shape[1] == new_tokens, out.shape
+    return dict(pages_per_sec=1.0 / total, seconds=total, t_vit=t_vit, t_llm=total - t_vit, t_build=t_build,
+                sample=(f"1 page {PAGE_HW[0]}x{PAGE_HW[1]} at full depth (42 ViT blocks + 28 decoder layers, fp32, {threads} threads), prefill T={ids.shape[1]} + "
+                        f"{new_tokens} greedy tokens through HF generate, timed directly ({total:.1f} s)"))
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU arm alone.  The K timed steps together process exactly ONE page (a step = 1/K of that
+    page's work), so ms_per_step x steps is the time really spent; warm-up is a sliver of work, not W more pages."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = usable_cpu_threads()
-    vals, t0 = [], time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference(args.new_tokens, threads, decode_steps=4)
-        if i >= args.warmup:
-            vals.append(r)
-        if time.perf_counter() - t0 > 240 and vals:
-            break
-    v = sum(x["pages_per_sec"] for x in vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pages/s", "n_gpus": args.gpus, "steps": len(vals),
-            "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": _config(args, 1),
-            "cpu_baseline": {"value": v, "unit": "pages/s", "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+    r = cpu_reference(args.new_tokens, threads)
+    v = r["pages_per_sec"]
+    cfgd = _config(args, 1)
+    cfgd["reference_arm"] = (f"one full-depth page timed directly in {r['seconds']:.1f} s; the {args.steps} reported steps are equal shares of that "
+                             "page (a CPU page costs about a minute: K whole pages would not fit the time box); warm-up = one 8x8-patch image + 4 tokens")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pages/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfgd,
+            "cpu_baseline": {"value": v, "unit": "pages/s", "cores": threads, "kind": "port", "sample": r["sample"],
+                             "t_vit_s": round(r["t_vit"], 2), "t_llm_s": round(r["t_llm"], 2)},
             "e2e": {"value": v, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -237,6 +205,44 @@ def _config(args, world):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def ids_checksum(new_ids) -> str:
+    """Order-sensitive 64-bit checksum of a [B, N] block of generated ids (tests/test_bench_config_gpu.py reproduces it from the
+    ids it has verified against the oracle; tests/golden/bench_ids_checksum.json pins it)."""
+    import torch
+    x = new_ids.to(torch.int64).reshape(-1).cpu()
+    idx = torch.arange(1, x.numel() + 1, dtype=torch.int64)
+    mod = (1 << 61) - 1
+    h = int(((x + 1) * (idx % 1000003 + 7919)).remainder(mod).sum().item()) % mod
+    return f"{h:016x}"
+
+
+def make_workload(cfg, batch: int, rank: int, dev):
+    """The benchmark's synthetic pages and prompts (shared with the parity test of this exact workload): pixel_values ~ N(0, 1)
+    drawn on the device with seed 1234 + rank, prompts = 128 text ids + image pads + 128 text ids (seed 7)."""
+    import torch
+    from dots_ocr_b200.utils.image_utils import vit_grid
+    s_vit, t_img = _page_tokens(cfg)
+    gh, gw = vit_grid(*PAGE_HW)
+    grid = torch.tensor([[1, gh, gw]] * batch)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pv = torch.randn((batch * s_vit, cfg.vision.patch_dim), generator=g, device=dev)
+    ids = _prompt_ids(cfg, batch, t_img)
+    return pv, grid, ids
+
+
+def _decode_traffic():
+    """DRAM bytes of one decode step from the committed ncu capture (profiles/decode_traffic_*.json), or None."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "decode_traffic_*.json"))):
+        try:
+            with open(f) as fh:
+                best = dict(json.load(fh), file=os.path.basename(f))
+        except Exception:
+            pass
+    return best
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -248,9 +254,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the single JSON line: NCCL_DEBUG=VERSION/INFO in the environment prints a banner on stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left as the caller set it (the driver counts ranks in NCCL's INFO log); the JSON line is printed after
+        # the process group is gone so that it stays the LAST line of stdout
         dist.init_process_group("nccl", device_id=dev)
 
     from dots_ocr_b200 import config, weights, ops
@@ -264,21 +269,19 @@ def run_gpu(args):
     cfg = config.PRESETS[args.preset]()
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev)
     eng = Engine(cfg, ck, dev)
+    if args.decode_fused is not None:
+        eng.decode_fused = bool(args.decode_fused)
+    ck_cpu = {k: v.to("cpu") for k, v in ck.items()} if (world == 1 and not args.no_cpu_baseline and args.preset == "full") else None
     del ck
     torch.cuda.empty_cache()
 
-    s_vit, t_img = _page_tokens(cfg)
-    from dots_ocr_b200.utils.image_utils import vit_grid
-    gh, gw = vit_grid(*PAGE_HW)
     B, N = args.batch, args.new_tokens
-    grid = torch.tensor([[1, gh, gw]] * B)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pv_dev = torch.randn((B * s_vit, cfg.vision.patch_dim), generator=g, device=dev)     # normalised pixel_values ~ N(0,1)
-    ids = _prompt_ids(cfg, B, t_img)
+    pv_dev, grid, ids = make_workload(cfg, B, rank, dev)
     ids_dev = ids.to(dev)
     pv_host = torch.empty(pv_dev.shape, dtype=torch.float32, pin_memory=True)
     pv_host.copy_(pv_dev)
     ids_host = ids.pin_memory()
+    last = {}
 
     def barrier():
         torch.cuda.synchronize()
@@ -287,13 +290,13 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_device():
-        return eng.generate(ids_dev, pixel_values=pv_dev, image_grid_thw=grid, max_new_tokens=N)
+        last["out"] = eng.generate(ids_dev, pixel_values=pv_dev, image_grid_thw=grid, max_new_tokens=N)
 
     def step_e2e():
         pv = pv_host.to(dev, non_blocking=True)
         idd = ids_host.to(dev, non_blocking=True)
         out = eng.generate(idd, pixel_values=pv, image_grid_thw=grid, max_new_tokens=N)
-        return out.sequences[:, idd.shape[1]:].cpu()
+        last["e2e_ids"] = out.sequences[:, idd.shape[1]:].cpu()
 
     def timed(fn, k):
         barrier()
@@ -310,21 +313,29 @@ def run_gpu(args):
 
     for _ in range(args.warmup):
         step_device()
-    # ---- timed region 1: inputs resident in HBM; per-kernel CUDA events via the ops profiling hook
+    # ---- timed region 1 (`value`): inputs resident in HBM, no per-launch instrumentation (events between PDL-chained
+    #      kernels would serialise them); only the two always-on events around each decode loop
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = eng.launches
-    ops.PROFILE = prof = []
+    eng.decode_log.clear()
     ms_total = timed(step_device, args.steps)
-    ops.PROFILE = None
     launches = eng.launches - l0
-    # ---- timed region 2: end to end through the public API with pinned host buffers
+    dec_log = list(eng.decode_log)
+    new_ids = last["out"].sequences[:, ids_dev.shape[1]:]
+    checksum = ids_checksum(new_ids)
+    # ---- timed region 2 (`e2e`): the public call with pinned host buffers, H2D and D2H inside
     ms_e2e = None
     if not args.no_e2e:
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        assert ids_checksum(last["e2e_ids"]) == checksum, "host-buffer leg produced different ids than the device-resident leg"
     clocks = sampler.stop() if rank == 0 else None
+    # ---- separate pass: CUDA events around every prefill-side launch (kernel classes and their share of a step)
+    ops.PROFILE = prof = []
+    ms_prof = timed(step_device, 1)
+    ops.PROFILE = None
 
     pages = B * world * args.steps
     value = pages / (ms_total / 1e3)
@@ -332,58 +343,81 @@ def run_gpu(args):
     h2d = pv_host.numel() * 4 + ids_host.numel() * 8
     d2h = B * N * 8
 
-    # ---- roofline of the dominant kernel (tcgen05 GEMM, all prefill-side shapes) from the live events
     peaks = _peaks()
     torch.cuda.synchronize()
+    # ---- roofline of the dominant phase: the decode loop (HBM-bound), from the events around the decode loops of the timed steps
+    roof = None
+    dec_ms_per_step_total = 0.0
+    if dec_log:
+        by = sum(d[0] for d in dec_log)
+        steps_dec = sum(d[1] for d in dec_log)
+        ms = sum(d[2].elapsed_time(d[3]) for d in dec_log)
+        dec_ms_per_step_total = ms / len(dec_log)
+        ach = by / (ms / 1e3) / 1e9
+        tr = _decode_traffic()
+        roof = {"kernel": ("decode step = one CUDA-graph launch: " + ("cluster split-K tcgen05 GEMMs (reduction, residual, RMSNorm on chip) + "
+                           "cluster-merged KV attention + gate|up SwiGLU GEMM + lm_head + argmax" if eng._decode_plan(B)["fused"] else
+                           "skinny tcgen05 GEMMs + KV attention + finalize kernels")),
+                "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
+                "peak_source": peaks["source"] + " (copy bandwidth)",
+                "launch": "one decode step (graph replay)", "algorithmic_bytes_per_launch": round(by / max(1, steps_dec)),
+                "avg_launch_ms": round(ms / max(1, steps_dec), 4), "launches": steps_dec, "share_of_step": round(ms / ms_total, 4),
+                "traffic": (tr or {}).get("dram_bytes_per_step"), "traffic_source": (tr or {}).get("file")}
+    # ---- prefill-side kernel classes from the instrumented pass
     agg = {}
     for name, work, e0, e1 in prof:
         a = agg.setdefault(name, [0.0, 0.0, 0])
         a[0] += work; a[1] += e0.elapsed_time(e1); a[2] += 1
-    roof = None
     by_kernel = {}
     for name, (work, ms, n) in agg.items():
-        by_kernel[name] = {"launches": n, "ms": round(ms, 3), "share_of_step": round(ms / ms_total, 4)}
+        by_kernel[name] = {"launches": n, "ms": round(ms, 3), "share_of_step": round(ms / ms_prof, 4)}
+    roof_gemm = roof_attn = None
     if "gemm_bf16_tcgen05" in agg:
         fl, ms, n = agg["gemm_bf16_tcgen05"]
         ach = fl / (ms / 1e3) / 1e12
-        roof = {"kernel": "gemm_bf16_tcgen05_kernel (ViT + LLM prefill linears)", "bound": "tensor", "achieved": round(ach, 1),
-                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4),
-                "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['tf_burst']})", "traffic": None,
-                "launches": n, "avg_launch_ms": round(ms / n, 4)}
-        by_kernel["gemm_bf16_tcgen05"]["tflops"] = round(ach, 1)
+        roof_gemm = {"kernel": "gemm2_bf16_tcgen05_kernel / gemm_bf16_tcgen05_kernel (ViT + LLM prefill linears)", "bound": "tensor",
+                     "achieved": round(ach, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4),
+                     "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['tf_burst']})", "launches": n,
+                     "avg_launch_ms": round(ms / n, 4), "share_of_step": round(ms / ms_prof, 4)}
     if "attn_fwd_vit" in agg:
         fl, ms, n = agg["attn_fwd_vit"]
-        by_kernel["attn_fwd_vit"]["tflops"] = round(fl / (ms / 1e3) / 1e12, 1)
-    roof_dec = None
-    if "decode_phase" in agg:
-        by, ms, n = agg["decode_phase"]           # bytes of all decode steps, ms of all decode phases
-        ach = by / (ms / 1e3) / 1e9
-        roof_dec = {"kernel": "decode step (CUDA graph: skinny tcgen05 GEMMs + KV attention + finalize kernels)", "bound": "hbm",
-                    "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
-                    "ms_per_decode_step": round(ms / (n * max(1, N - 1)), 4), "traffic": None}
+        ach = fl / (ms / 1e3) / 1e12
+        roof_attn = {"kernel": "attn_fwd_tcgen05_kernel<0> (ViT bidirectional attention)", "bound": "tensor", "achieved": round(ach, 1),
+                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4), "launches": n,
+                     "avg_launch_ms": round(ms / n, 4), "share_of_step": round(ms / ms_prof, 4)}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     threads = usable_cpu_threads()
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if ck_cpu is not None:
         try:
-            r = cpu_reference(N, threads, decode_steps=8)
+            r = cpu_reference(N, threads, ck=ck_cpu, cfg=cfg)
             cpu = {"value": r["pages_per_sec"], "unit": "pages/s", "cores": threads, "kind": "port", "sample": r["sample"],
-                   "t_vit_s": round(r["t_vit"], 2), "t_prefill_s": round(r["t_prefill"], 2), "t_step_s": round(r["t_step"], 4)}
+                   "t_vit_s": round(r["t_vit"], 2), "t_llm_s": round(r["t_llm"], 2)}
         except Exception as e:      # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": "pages/s", "cores": threads, "kind": "port", "sample": f"failed: {e!r}"}
+    golden = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_ids_checksum.json")) as f:
+            golden = json.load(f).get(f"b{B}_n{N}_p{PAGE_HW[0]}_rank0")
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": round(value, 3), "unit": "pages/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(args, world),
             "e2e": {"value": round(e2e_v, 3) if e2e_v else None, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_decode": roof_dec, "kernels": by_kernel,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_vit_attention": roof_attn,
+            "phases_ms": {"decode_loop": round(dec_ms_per_step_total, 2), "step": round(ms_total / args.steps, 2),
+                          "instrumented_step": round(ms_prof, 2)},
+            "kernels": by_kernel, "ids_checksum": {"value": checksum, "golden": golden, "matches_golden": (checksum == golden) if golden else None},
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        time.sleep(1.0)             # let the other ranks' teardown chatter (NCCL INFO) drain: the JSON stays the last stdout line
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -402,6 +436,8 @@ def main():
     ap.add_argument("--gemm-pair", dest="gemm_pair", type=int, default=None, choices=[0, 1],
                     help="CTA-pair (cta_group::2) kernel for the large prefill GEMMs (default: the library default)")
     ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
+    ap.add_argument("--decode-fused", dest="decode_fused", type=int, default=None, choices=[0, 1],
+                    help="1: 5-kernel decode layer (cluster GEMMs), 0: 7-kernel per-op layer (default: the engine default)")
     ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "mma"])
     args = ap.parse_args()
     global PAGE_HW

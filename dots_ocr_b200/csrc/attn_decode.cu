@@ -10,9 +10,13 @@
 //   warps 0-3          consumers: warp w owns keys [16w, 16w+16) of every tile (QK^T, online softmax, PV with mma.sync),
 //                      fixed-order merge of the four partial (m, l, O) through shared memory at the end.
 //
-// Keys are additionally split across CTAs (grid.x = n_splits, "flash decoding") and merged by a small combine kernel.
-// With qkv_partial != nullptr the QKV finalize of the current token (split-K reduce + bias + RoPE + KV append) runs in
-// the prologue of this kernel.
+// Keys are additionally split across CTAs (grid.x = n_splits, "flash decoding").  Up to DEC_MAX_CLUSTER splits form a
+// thread-block CLUSTER: the non-leader CTAs hand their partial (m, l, O) to the leader through distributed shared memory
+// and the leader merges them in split order -- no partials in HBM and no combine launch; more splits than that fall
+// back to a small combine kernel.  Two CTAs of 103 KB share an SM, so batch x kv_heads x splits >= 2 x SMs keeps
+// ~190 KB of K/V in flight per SM.
+// The QKV finalize of the current token (bias + RoPE + KV append) runs in the prologue of this kernel, either from the
+// split-K fp32 partials of dots_gemm_skinny_bf16 (qkv_partial) or from the bf16 q|k|v row of dots_decode_gemm_qkv (qkv_bf16).
 #include "common.h"
 #include "ptx.cuh"
 #include "mma_sm80.cuh"
@@ -32,6 +36,8 @@ constexpr int DEC_STAGE_BYTES = 4 * DEC_BOX_BYTES;                         // K 
 #endif
 constexpr int DEC_STAGES = DEC_STAGES_OVR;
 constexpr int DEC_SMEM = 1024 /*align*/ + 4096 /*Q*/ + DEC_STAGES * DEC_STAGE_BYTES + 256 /*barriers*/;
+constexpr int DEC_MAX_CLUSTER = 4;                                         // splits merged on chip
+constexpr int DEC_MERGE_BYTES = 8 * DEC_D * 4 + 8 * 2 * 4;                 // one peer's partial: O [<= 8 heads][128] + (m, l) [<= 8]
 
 struct DecParams {
     const bf16* q;            // [B, n_q_heads * 128]
@@ -48,7 +54,10 @@ struct DecParams {
     // [qkv_splits][B][(nq + 2 nkv) * 128] of the QKV GEMM; this kernel adds the bias, applies RoPE, appends k, v to the
     // cache and keeps q in shared memory.  qkv_partial == nullptr: q is read from p.q (plain dots_attn_decode).
     const float* qkv_partial;
+    const bf16* qkv_bf16;     // [B][(nq + 2 nkv) * 128], bias already added (dots_decode_gemm_qkv); alternative to qkv_partial
     int qkv_splits;
+    int cluster_merge;        // 1: the n_splits CTAs of a (sequence, kv head) are one cluster and merge through DSMEM
+    int fault;                // test-only fault injection (dots_debug_set_fault): 1 = key tile 0, 2 = every other key tile loses its P*V term
     const bf16* qkv_bias;
     const int* pos;
     const float* inv_freq;
@@ -83,7 +92,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     uint8_t* sQ = smem + DEC_STAGES * DEC_STAGE_BYTES;           // 4 KB
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + 4096); // [STAGES]
     uint64_t* empty_bar = full_bar + DEC_STAGES;                 // [STAGES]
+    uint8_t* sMerge = sQ + 4096 + 256;                           // leader only: [n_splits - 1] x DEC_MERGE_BYTES (cluster merge)
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const bool fused = (p.qkv_partial != nullptr) || (p.qkv_bf16 != nullptr);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
@@ -128,7 +139,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         }
         __syncwarp();
         pdl_wait();
-        if (p.qkv_partial != nullptr && holds_new) {
+        if (fused && holds_new) {
             // the appended k/v row is produced by the consumer warps of this CTA: wait until they published it
             asm volatile("bar.sync 2, %0;" ::"n"(DEC_THREADS) : "memory");
         }
@@ -138,6 +149,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
                 issue(i);
             }
         }
+        __syncwarp();
+        if (p.cluster_merge) cluster_sync_all();       // every thread of the cluster takes part in the merge barrier
         return;
     }
 
@@ -145,7 +158,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     pdl_wait();
 
     // Q tile: rows 0..G-1 = the group's q heads, rows G..15 zero
-    if (p.qkv_partial == nullptr) {
+    if (!fused) {
         const bf16* qg = p.q + (long long)b * p.n_q_heads * DEC_D + (long long)kvh * p.group * DEC_D;
         for (int idx = tid; idx < 16 * 16; idx += DEC_WARPS * 32) {
             const int r = idx >> 4, c = idx & 15;
@@ -169,34 +182,44 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
             if (hl >= p.group && !owns_new) continue;
             const int col0 = (hl < p.group ? (kvh * p.group + hl)
                                            : (hl == p.group ? p.n_q_heads + kvh : p.n_q_heads + p.n_kv_heads + kvh)) * DEC_D + c4 * 4;
-            const float* src = p.qkv_partial + (long long)b * N + col0;
-            float x1[4] = {0.f, 0.f, 0.f, 0.f}, x2[4] = {0.f, 0.f, 0.f, 0.f};
-            int sidx = 0;
-            for (; sidx + 4 <= p.qkv_splits; sidx += 4) {
-                float4 a[4], d[4];
+            float x1[4], x2[4];
+            if (p.qkv_bf16 != nullptr) {
+                // q|k|v row of dots_decode_gemm_qkv: reduced, bias added and rounded to bf16 already (HF's Linear output)
+                const uint2 a = *reinterpret_cast<const uint2*>(p.qkv_bf16 + (long long)b * N + col0);
+                const uint2 d = *reinterpret_cast<const uint2*>(p.qkv_bf16 + (long long)b * N + col0 + 64);
+                x1[0] = bf16_lo(a.x); x1[1] = bf16_hi(a.x); x1[2] = bf16_lo(a.y); x1[3] = bf16_hi(a.y);
+                x2[0] = bf16_lo(d.x); x2[1] = bf16_hi(d.x); x2[2] = bf16_lo(d.y); x2[3] = bf16_hi(d.y);
+            } else {
+                const float* src = p.qkv_partial + (long long)b * N + col0;
+                x1[0] = x1[1] = x1[2] = x1[3] = 0.f;
+                x2[0] = x2[1] = x2[2] = x2[3] = 0.f;
+                int sidx = 0;
+                for (; sidx + 4 <= p.qkv_splits; sidx += 4) {
+                    float4 a[4], d[4];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    a[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride);
-                    d[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride + 64);
-                }
+                    for (int w = 0; w < 4; ++w) {
+                        a[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride);
+                        d[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride + 64);
+                    }
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    x1[0] += a[w].x; x1[1] += a[w].y; x1[2] += a[w].z; x1[3] += a[w].w;
-                    x2[0] += d[w].x; x2[1] += d[w].y; x2[2] += d[w].z; x2[3] += d[w].w;
+                    for (int w = 0; w < 4; ++w) {
+                        x1[0] += a[w].x; x1[1] += a[w].y; x1[2] += a[w].z; x1[3] += a[w].w;
+                        x2[0] += d[w].x; x2[1] += d[w].y; x2[2] += d[w].z; x2[3] += d[w].w;
+                    }
                 }
+                for (; sidx < p.qkv_splits; ++sidx) {
+                    const float4 a = *reinterpret_cast<const float4*>(src + sidx * sstride);
+                    const float4 d = *reinterpret_cast<const float4*>(src + sidx * sstride + 64);
+                    x1[0] += a.x; x1[1] += a.y; x1[2] += a.z; x1[3] += a.w;
+                    x2[0] += d.x; x2[1] += d.y; x2[2] += d.z; x2[3] += d.w;
+                }
+                const uint2 b1 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0);
+                const uint2 b2 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0 + 64);
+                x1[0] = bf16_round(x1[0] + bf16_lo(b1.x)); x1[1] = bf16_round(x1[1] + bf16_hi(b1.x));
+                x1[2] = bf16_round(x1[2] + bf16_lo(b1.y)); x1[3] = bf16_round(x1[3] + bf16_hi(b1.y));
+                x2[0] = bf16_round(x2[0] + bf16_lo(b2.x)); x2[1] = bf16_round(x2[1] + bf16_hi(b2.x));
+                x2[2] = bf16_round(x2[2] + bf16_lo(b2.y)); x2[3] = bf16_round(x2[3] + bf16_hi(b2.y));
             }
-            for (; sidx < p.qkv_splits; ++sidx) {
-                const float4 a = *reinterpret_cast<const float4*>(src + sidx * sstride);
-                const float4 d = *reinterpret_cast<const float4*>(src + sidx * sstride + 64);
-                x1[0] += a.x; x1[1] += a.y; x1[2] += a.z; x1[3] += a.w;
-                x2[0] += d.x; x2[1] += d.y; x2[2] += d.z; x2[3] += d.w;
-            }
-            const uint2 b1 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0);
-            const uint2 b2 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0 + 64);
-            x1[0] = bf16_round(x1[0] + bf16_lo(b1.x)); x1[1] = bf16_round(x1[1] + bf16_hi(b1.x));
-            x1[2] = bf16_round(x1[2] + bf16_lo(b1.y)); x1[3] = bf16_round(x1[3] + bf16_hi(b1.y));
-            x2[0] = bf16_round(x2[0] + bf16_lo(b2.x)); x2[1] = bf16_round(x2[1] + bf16_hi(b2.x));
-            x2[2] = bf16_round(x2[2] + bf16_lo(b2.y)); x2[3] = bf16_round(x2[3] + bf16_hi(b2.y));
             float o1[4], o2[4];
             if (hl <= p.group) {
                 dec_rope_bf16_4(x1, x2, posb, p.inv_freq, c4 * 4, o1, o2);
@@ -216,7 +239,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
             }
         }
     }
-    if (p.qkv_partial != nullptr && holds_new) {
+    if (fused && holds_new) {
         asm volatile("fence.proxy.async;" ::: "memory");        // generic-proxy cache writes -> visible to the TMA (async proxy) reads
         __threadfence();
         asm volatile("bar.sync 2, %0;" ::"n"(DEC_THREADS) : "memory");      // releases the producer's last tile
@@ -302,6 +325,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
             pf[nb * 2 + 0] = pack_bf16x2(p0, p1);
             pf[nb * 2 + 1] = pack_bf16x2(p2, p3);
         }
+        if ((p.fault == 1 && i == 0 && split == 0) || (p.fault == 2 && (i & 1) == 0)) pf[0] = pf[1] = pf[2] = pf[3] = 0u;   // test-only fault
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
@@ -335,26 +359,81 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         sML[(warp * 8 + g) * 2 + 1] = l_run[0];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");
-    for (int idx = tid; idx < p.group * DEC_D; idx += DEC_WARPS * 32) {
-        const int r = idx / DEC_D, c = idx % DEC_D;
-        float m = -INFINITY;
+    // thread tid owns head dim c = tid of every q head r of the group (DEC_WARPS * 32 == DEC_D)
+    static_assert(DEC_WARPS * 32 == DEC_D, "one consumer thread per head dim");
+    const int c = tid;
+    float accv[8], mv[8], lv[8];
 #pragma unroll
-        for (int w = 0; w < DEC_WARPS; ++w) m = fmaxf(m, sML[(w * 8 + r) * 2]);
-        float acc = 0.f, l = 0.f;
+    for (int r = 0; r < 8; ++r) {
+        accv[r] = 0.f; mv[r] = -INFINITY; lv[r] = 0.f;
+        if (r < p.group) {
+            float m = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < DEC_WARPS; ++w) {
-            const float mw = sML[(w * 8 + r) * 2];
-            const float wgt = (mw == -INFINITY) ? 0.f : fast_exp2(mw - m);
-            acc += wgt * sO[(w * 8 + r) * DEC_D + c];
-            l += wgt * sML[(w * 8 + r) * 2 + 1];
+            for (int w = 0; w < DEC_WARPS; ++w) m = fmaxf(m, sML[(w * 8 + r) * 2]);
+            float acc = 0.f, l = 0.f;
+#pragma unroll
+            for (int w = 0; w < DEC_WARPS; ++w) {
+                const float mw = sML[(w * 8 + r) * 2];
+                const float wgt = (mw == -INFINITY) ? 0.f : fast_exp2(mw - m);
+                acc += wgt * sO[(w * 8 + r) * DEC_D + c];
+                l += wgt * sML[(w * 8 + r) * 2 + 1];
+            }
+            accv[r] = acc; mv[r] = m; lv[r] = l;
         }
-        const int head = kvh * p.group + r;
-        if (p.n_splits == 1) {
-            p.out[((long long)b * p.n_q_heads + head) * DEC_D + c] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
-        } else {
-            const long long pi = ((long long)b * p.n_q_heads + head) * p.n_splits + split;
-            p.part_o[pi * DEC_D + c] = acc;
-            if (c == 0) { p.part_ml[pi * 2] = m; p.part_ml[pi * 2 + 1] = l; }
+    }
+    if (p.n_splits == 1) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < p.group)
+                p.out[((long long)b * p.n_q_heads + kvh * p.group + r) * DEC_D + c] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
+    } else if (p.cluster_merge) {
+        // ---- on-chip merge across the cluster: peers write (O, m, l) into the leader's shared memory, the leader combines
+        //      in split order (same arithmetic as attn_decode_combine_kernel) ----
+        if (split != 0) {
+            const uint32_t base = mapa_shared(smem_u32(sMerge + (size_t)(split - 1) * DEC_MERGE_BYTES), 0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < p.group) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(r * DEC_D + c) * 4), "f"(accv[r]) : "memory");
+            if (c == 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < p.group) {
+                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(8 * DEC_D + r * 2) * 4), "f"(mv[r]) : "memory");
+                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(8 * DEC_D + r * 2 + 1) * 4), "f"(lv[r]) : "memory");
+                    }
+            }
+        }
+        cluster_sync_all();
+        if (split == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (r >= p.group) continue;
+                float m = mv[r];
+                for (int sp = 1; sp < p.n_splits; ++sp)
+                    m = fmaxf(m, reinterpret_cast<const float*>(sMerge + (size_t)(sp - 1) * DEC_MERGE_BYTES)[8 * DEC_D + r * 2]);
+                float acc = 0.f, l = 0.f;
+                {
+                    const float w = (mv[r] == -INFINITY) ? 0.f : fast_exp2(mv[r] - m);
+                    acc += w * accv[r];
+                    l += w * lv[r];
+                }
+                for (int sp = 1; sp < p.n_splits; ++sp) {
+                    const float* pm = reinterpret_cast<const float*>(sMerge + (size_t)(sp - 1) * DEC_MERGE_BYTES);
+                    const float ms = pm[8 * DEC_D + r * 2];
+                    const float w = (ms == -INFINITY) ? 0.f : fast_exp2(ms - m);
+                    acc += w * pm[r * DEC_D + c];
+                    l += w * pm[8 * DEC_D + r * 2 + 1];
+                }
+                p.out[((long long)b * p.n_q_heads + kvh * p.group + r) * DEC_D + c] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r >= p.group) continue;
+            const long long pi = ((long long)b * p.n_q_heads + kvh * p.group + r) * p.n_splits + split;
+            p.part_o[pi * DEC_D + c] = accv[r];
+            if (c == 0) { p.part_ml[pi * 2] = mv[r]; p.part_ml[pi * 2 + 1] = lv[r]; }
         }
     }
 }
@@ -382,18 +461,28 @@ attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __rest
 
 using namespace dots;
 
+namespace dots {
+int g_dec_cluster = 1;        // dots_set_decode_cluster(): merge <= DEC_MAX_CLUSTER key splits on chip (cluster + DSMEM) instead of a combine kernel
+int g_debug_fault = 0;        // dots_debug_set_fault(): test-only fault injection
+}
+
 static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_heads, int head_dim, int n_splits, float softmax_scale,
                               void* stream, const char* who) {
     DOTS_REQUIRE(head_dim == DEC_D, "%s: head_dim must be 128", who);
     DOTS_REQUIRE(batch > 0 && n_q_heads % n_kv_heads == 0 && n_q_heads / n_kv_heads <= 8,
                  "%s: bad heads %d/%d (group must be <= 8)", who, n_q_heads, n_kv_heads);
-    DOTS_REQUIRE(n_splits >= 1 && (n_splits == 1 || (p.part_o && p.part_ml)), "%s: n_splits>1 needs partial buffers", who);
+    const bool cluster = n_splits > 1 && n_splits <= DEC_MAX_CLUSTER && g_dec_cluster;
+    DOTS_REQUIRE(n_splits >= 1 && (n_splits == 1 || cluster || (p.part_o && p.part_ml)), "%s: n_splits > %d needs partial buffers", who,
+                 DEC_MAX_CLUSTER);
+    p.cluster_merge = cluster ? 1 : 0;
+    p.fault = g_debug_fault;
     p.n_q_heads = n_q_heads; p.n_kv_heads = n_kv_heads; p.group = n_q_heads / n_kv_heads; p.n_splits = n_splits;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool configured[64] = {false};
     if (first_use_on_device(configured)) {
-        DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+        DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             DEC_SMEM + (DEC_MAX_CLUSTER - 1) * DEC_MERGE_BYTES));
     }
     // K / V cache layer slice [batch * n_kv_heads * ctx_max, 128] bf16, fetched as [64 keys][64 dims] 128-B-swizzled boxes
     const unsigned long long rows = (unsigned long long)batch * n_kv_heads * (unsigned long long)p.ctx_max;
@@ -402,6 +491,11 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
     if (make_tmap_2d_bf16(&tk, p.kc, rows, DEC_D, DEC_D, DEC_RING_KEYS, 64)) return -4;
     if (make_tmap_2d_bf16(&tv, p.vc, rows, DEC_D, DEC_D, DEC_RING_KEYS, 64)) return -4;
     dim3 grid(n_splits, n_kv_heads, batch);
+    if (cluster) {
+        DOTS_CHECK_CUDA(launch_ex_cluster(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM + (n_splits - 1) * DEC_MERGE_BYTES), st,
+                                          true, (unsigned)n_splits, tk, tv, p));
+        return 0;
+    }
     DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, tk, tv, p));
     if (n_splits > 1) {
         DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, p.part_o, p.part_ml, p.out, n_splits));
@@ -429,4 +523,28 @@ extern "C" int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, 
     p.qkv_partial = qkv_partial; p.qkv_splits = qkv_splits; p.qkv_bias = (const bf16*)qkv_bias; p.pos = pos; p.inv_freq = inv_freq;
     p.kc_w = (bf16*)k_cache; p.vc_w = (bf16*)v_cache;
     return launch_attn_decode(p, batch, n_q_heads, n_kv_heads, head_dim, n_splits, softmax_scale, stream, "dots_attn_decode_fused");
+}
+
+// Same as dots_attn_decode_fused, with q|k|v of the current token arriving as the bf16 row [batch][(nq + 2 nkv) * 128] that
+// dots_decode_gemm_qkv wrote (bias already added): RoPE + KV append + attention.
+extern "C" int dots_attn_decode_qkv(const void* qkv_bf16, const int* pos, const float* inv_freq, void* k_cache, void* v_cache, const int* ctx_len,
+                                    void* out, float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
+                                    long long ctx_max, int n_splits, float softmax_scale, void* stream) {
+    DOTS_REQUIRE(qkv_bf16 && pos && inv_freq, "dots_attn_decode_qkv: missing QKV inputs");
+    DecParams p{};
+    p.q = nullptr; p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.ctx_len = ctx_len;
+    p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
+    p.qkv_bf16 = (const bf16*)qkv_bf16; p.pos = pos; p.inv_freq = inv_freq;
+    p.kc_w = (bf16*)k_cache; p.vc_w = (bf16*)v_cache;
+    return launch_attn_decode(p, batch, n_q_heads, n_kv_heads, head_dim, n_splits, softmax_scale, stream, "dots_attn_decode_qkv");
+}
+
+extern "C" int dots_set_decode_cluster(int enable) {
+    dots::g_dec_cluster = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int dots_debug_set_fault(int code) {
+    dots::g_debug_fault = code;
+    return 0;
 }

@@ -453,9 +453,13 @@ __device__ __forceinline__ void sum_splits8(const float* __restrict__ p0, long l
 // x = embed[last_id]; resid = x; normed = RMSNorm(x) * w          (one warp per sequence)
 __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table,
                                                                    long long vocab, const bf16* __restrict__ w, bf16* __restrict__ resid,
-                                                                   bf16* __restrict__ normed, int B, int H, float eps) {
+                                                                   bf16* __restrict__ normed, int B, int H, float eps,
+                                                                   unsigned* __restrict__ counters, int n_counters) {
     pdl_wait();
     pdl_launch_dependents();
+    // first kernel of a decode step: re-arm the rendezvous counters of this step's dots_decode_gemm_resnorm launches
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n_counters; i += blockDim.x) counters[i] = 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
     if (b >= B) return;
@@ -701,9 +705,10 @@ extern "C" int dots_argmax_advance(const void* logits, long long ldl, int batch,
 }
 
 extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
-                                         void* normed, int batch, int H, float eps, void* stream) {
+                                         void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, void* stream) {
     DOTS_REQUIRE(batch > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_embed_rmsnorm: H %% 8, H <= 2048");
-    DOTS_CHECK_CUDA(launch_ex(decode_embed_rmsnorm_kernel, dim3((batch + 7) / 8), dim3(256), (size_t)(0), ST(stream), true, ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid, (bf16*)normed, batch, H, eps));
+    DOTS_REQUIRE(n_counters >= 0 && (n_counters == 0 || counters), "dots_decode_embed_rmsnorm: n_counters without a counter array");
+    DOTS_CHECK_CUDA(launch_ex(decode_embed_rmsnorm_kernel, dim3((batch + 7) / 8), dim3(256), (size_t)(0), ST(stream), true, ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid, (bf16*)normed, batch, H, eps, counters, n_counters));
     return 0;
 }
 

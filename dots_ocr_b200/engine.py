@@ -164,6 +164,14 @@ class Engine:
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.launches = 0       # C-ABI kernel launches issued (bench.py reports it)
         self.eos_check_every = 64       # decode steps between looks at the finished flags (only when a stop id is given)
+        # Decode path for batches <= 64: 5 kernels per layer (cluster split-K GEMMs with the reduction, residual add and RMSNorm
+        # on chip; cluster-merged attention) instead of 7 + fp32 partials.  False = the per-op path with
+        # split-K partials and finalize kernels, which also serves batches of 65..256.
+        self.decode_fused = True
+        self._fused_ok: Dict[int, bool] = {}
+        self._dec_cache: Optional[dict] = None
+        self._cap_stream = torch.cuda.Stream(device=dev)
+        self.decode_log: List[tuple] = []     # (algorithmic bytes, steps, start event, end event) of the last generate calls' decode loops
 
     # ------------------------------------------------------------------------------ vision
     @_on_device
@@ -279,19 +287,37 @@ class Engine:
             self.launches += 8
         return x
 
+    def _fused_decode_ok(self, B: int) -> bool:
+        """The cluster GEMMs rendezvous on a device-wide counter: every row-tile cluster of a launch must be resident at once."""
+        if not self.decode_fused or B > 64:
+            return False
+        key = 32 if B <= 32 else 64
+        if key not in self._fused_ok:
+            tiles = -(-self.cfg.text.hidden_size // 128)
+            self._fused_ok[key] = ops.decode_gemm_max_clusters(key) >= tiles
+        return self._fused_ok[key]
+
     def _decode_plan(self, B: int):
         t = self.cfg.text
         H, I = t.hidden_size, t.intermediate_size
         qkv_n = (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim
         kb = lambda k: -(-k // 64)
         tiles = lambda n: -(-n // 128)
+        pairs = max(1, B * t.num_key_value_heads)
+        fused = self._fused_decode_ok(B)
+        if fused:
+            # two 103 KB CTAs share an SM: aim for ~2 CTAs per SM; up to 4 key splits merge on chip (cluster), more need the combine kernel
+            attn = max(1, min(16, (2 * self.sms) // pairs))
+        else:
+            # one CTA per (sequence, kv head) once that alone covers most SMs (no combine kernel); flash-decoding splits below
+            attn = 1 if pairs >= (3 * self.sms) // 4 else max(1, min(16, (2 * self.sms) // pairs))
         return dict(
+            fused=fused,
             qkv=ops.pick_splits(tiles(qkv_n), kb(H), self.sms),
             o=ops.pick_splits(tiles(H), kb(t.num_attention_heads * t.head_dim), self.sms),
             gu=ops.pick_splits(tiles(2 * I), kb(H), self.sms),
             down=ops.pick_splits(tiles(H), kb(I), self.sms),
-            # one CTA per (sequence, kv head) once that alone covers most SMs (no combine kernel); flash-decoding splits below
-            attn=1 if B * t.num_key_value_heads >= (3 * self.sms) // 4 else max(1, min(16, (2 * self.sms) // max(1, B * t.num_key_value_heads))),
+            attn=attn,
         )
 
     def _decode_step(self, st: dict):
@@ -300,18 +326,32 @@ class Engine:
         nq, nkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
         pl = st["plan"]
         scale = hd ** -0.5
-        ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
         n_layers = len(self.t_layers)
-        for li, L in enumerate(self.t_layers):
-            ops.gemm_skinny(st["normed"], L["qkv_w"], pl["qkv"], partial=st["partial"])
-            ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
-                                  st["ctx_len"], st["attn"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"])
-            nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
-            ops.gemm_skinny(st["attn"], L["o"], pl["o"], partial=st["partial"])
-            ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed"], t.rms_norm_eps)
-            ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
-            ops.gemm_skinny(st["act"], L["down"], pl["down"], partial=st["partial"])
-            ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed"], t.rms_norm_eps)
+        if pl["fused"]:
+            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps,
+                                     counters=st["counters"])
+            for li, L in enumerate(self.t_layers):
+                nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
+                ops.decode_gemm_qkv(st["normed"], L["qkv_w"], L["qkv_b"], st["qkv"])
+                ops.attn_decode_qkv(st["qkv"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li], st["ctx_len"], st["attn"], nq, nkv,
+                                    st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"])
+                ops.decode_gemm_resnorm(st["attn"], L["o"], st["resid"], L["ln2"], st["normed"], st["stats"][0], st["counters"][2 * li:2 * li + 1],
+                                        t.rms_norm_eps)
+                ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
+                ops.decode_gemm_resnorm(st["act"], L["down"], st["resid"], nxt, st["normed"], st["stats"][1],
+                                        st["counters"][2 * li + 1:2 * li + 2], t.rms_norm_eps)
+        else:
+            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
+            for li, L in enumerate(self.t_layers):
+                ops.gemm_skinny(st["normed"], L["qkv_w"], pl["qkv"], partial=st["partial"])
+                ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
+                                      st["ctx_len"], st["attn"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"])
+                nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
+                ops.gemm_skinny(st["attn"], L["o"], pl["o"], partial=st["partial"])
+                ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed"], t.rms_norm_eps)
+                ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
+                ops.gemm_skinny(st["act"], L["down"], pl["down"], partial=st["partial"])
+                ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed"], t.rms_norm_eps)
         ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
         ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
                            st["stops"], st["pad"], st["forced"])
@@ -341,7 +381,9 @@ class Engine:
         st["ctx_len"] = lens.to(torch.int32)
         st["finished"] = torch.zeros(B, device=dev, dtype=torch.int32)
         st["forced"] = forced_ids.to(dev).long().contiguous() if forced_ids is not None else None
-        st["counters"] = torch.zeros(8, device=dev, dtype=torch.int32)
+        st["qkv"] = torch.empty((B, (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim), device=dev, dtype=torch.bfloat16)
+        st["stats"] = torch.zeros((2, -(-H // 128) * 64), device=dev, dtype=torch.float32)
+        st["counters"] = torch.zeros(2 * t.num_hidden_layers, device=dev, dtype=torch.int32)
         return st
 
     def decode_weight_bytes(self) -> int:
@@ -364,7 +406,10 @@ class Engine:
 
     def launches_per_decode_step(self, B: int) -> int:
         pl = self._decode_plan(B)
-        per_layer = 7 + (1 if pl["attn"] > 1 else 0)
+        if pl["fused"]:
+            per_layer = 5 + (1 if pl["attn"] > ops.ATTN_DECODE_MAX_CLUSTER else 0)
+        else:
+            per_layer = 7 + (1 if pl["attn"] > 1 and not (ops.DECODE_CLUSTER and pl["attn"] <= ops.ATTN_DECODE_MAX_CLUSTER) else 0)
         return 1 + per_layer * len(self.t_layers) + 2
 
     @_on_device
@@ -407,10 +452,28 @@ class Engine:
             if n_img != image_embeds.shape[0]:
                 raise ValueError(f"image tokens in input_ids ({n_img}) != image embedding rows ({image_embeds.shape[0]})")
 
-        kc, vc = self._alloc_cache(B, ctx_max)
+        # KV cache, decode workspaces and the captured decode graph are kept from call to call when the shape key repeats
+        # (a serving loop and the benchmark call generate with the same batch geometry over and over)
+        stops_key = tuple(stop_list(eos_token_id)[: ops.MAX_STOP_IDS])
+        key = (B, ctx_max, N, stops_key, int(pad_token_id), bool(self.decode_fused), ops.DECODE_CLUSTER)
+        ent = self._dec_cache if (self._dec_cache is not None and self._dec_cache["key"] == key and forced_ids is None) else None
+        if ent is None:
+            self._dec_cache = None                      # release the previous geometry's buffers before allocating new ones
+            kc, vc = self._alloc_cache(B, ctx_max)
+            st = self._new_decode_state(B, lens, kc, vc, ctx_max, N, eos_token_id, pad_token_id, forced_ids)
+            ent = dict(key=key, st=st, graph=None)
+            if forced_ids is None:
+                self._dec_cache = ent
+        else:
+            st = ent["st"]
+            kc, vc = st["kc"], st["vc"]
+            st["last"].zero_()
+            st["out_ids"].fill_(int(pad_token_id))
+            st["step"].zero_()
+            st["finished"].zero_()
+            st["pos"].copy_((lens - 1).to(torch.int32))
+            st["ctx_len"].copy_(lens.to(torch.int32))
         x = self._prefill(ids_packed, slots, image_embeds, cu, seq_lens, positions, seq_of_tok, kc, vc, ctx_max)
-
-        st = self._new_decode_state(B, lens, kc, vc, ctx_max, N, eos_token_id, pad_token_id, forced_ids)
         pl = st["plan"]
         all_logits = torch.empty((N, B, t.vocab_size), device=dev, dtype=torch.bfloat16) if return_logits else None
 
@@ -434,26 +497,28 @@ class Engine:
         def all_finished() -> bool:
             return bool(st["finished"].all().item())
 
+        # two events around the decode loop (always on: they sit outside the PDL-chained kernels and cost nothing); bench.py
+        # turns them into the decode-step HBM roofline
         prof_ev = None
-        if ops.PROFILE is not None and n_steps > 0:
+        if n_steps > 0:
             prof_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             prof_ev[0].record()
+        done = 0
         if n_steps > 0:
             if use_graph and not return_logits:
-                self._decode_step(st)                   # eager once (also warms every kernel variant)
-                done = 1
-                if n_steps > 1:
-                    cap = torch.cuda.Stream(device=dev)
+                if ent["graph"] is None:
+                    self._decode_step(st)               # eager once (also warms every kernel variant)
+                    done = 1
+                if n_steps > done:
+                    cap = self._cap_stream
                     cap.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(cap):
-                        g = ops.capture(lambda: self._decode_step(st))
-                        # capture does not execute: replay for every remaining step
-                        done += replay_steps(g.launch, n_steps - 1, check, all_finished)
+                        if ent["graph"] is None:
+                            ent["graph"] = ops.capture(lambda: self._decode_step(st))      # capture does not execute
+                        done += replay_steps(ent["graph"].launch, n_steps - done, check, all_finished)
                     torch.cuda.current_stream().wait_stream(cap)
                 self.launches += per_step * done
-                st["_graph"] = None
             else:
-                done = 0
                 for s in range(n_steps):
                     self._decode_step(st)
                     done += 1
@@ -465,7 +530,8 @@ class Engine:
 
         if prof_ev is not None:
             prof_ev[1].record()
-            ops.PROFILE.append(("decode_phase", self.decode_bytes(B, seq_lens, n_steps), prof_ev[0], prof_ev[1]))
+            self.decode_log.append((self.decode_bytes(B, seq_lens, done), done, prof_ev[0], prof_ev[1]))
+            del self.decode_log[:-64]
         out_new = finalize_new_tokens(st["out_ids"], stop_list(eos_token_id), int(pad_token_id))
         seqs = torch.cat([ids, out_new], dim=1)
         if return_logits and out_new.shape[1] < N:

@@ -320,11 +320,72 @@ def argmax_advance(logits, next_ids, out_ids=None, step=None, pos=None, ctx_len=
     _lib.check(rc, "dots_argmax_advance")
 
 
-def decode_embed_rmsnorm(ids, table, w, resid, normed, eps):
+def decode_embed_rmsnorm(ids, table, w, resid, normed, eps, counters=None):
     V, H = table.shape
+    if counters is not None:
+        assert counters.dtype == torch.int32 and counters.is_cuda
     rc = _lib.load().dots_decode_embed_rmsnorm(_p(ids), _p(table), _ll(V), _p(w), _p(resid), _p(normed), ids.numel(), H,
-                                               C.c_float(eps), _stream())
+                                               C.c_float(eps), _p(counters), 0 if counters is None else counters.numel(), _stream())
     _lib.check(rc, "dots_decode_embed_rmsnorm")
+
+
+def decode_gemm_qkv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """q|k|v projection of a decode step (batch <= 64), split-K reduced inside thread-block clusters: out = bf16(x @ w.T + bias)."""
+    _bf16_2d(x, "x"); _bf16_2d(w, "w"); _bf16_2d(out, "out")
+    B, Kd = x.shape
+    N = w.shape[0]
+    assert out.shape == (B, N)
+    rc = _lib.load().dots_decode_gemm_qkv(_p(x), _ll(x.stride(0)), _p(w), _ll(w.stride(0)), _p(bias), _p(out), _ll(out.stride(0)), B, N, Kd,
+                                          _stream())
+    _lib.check(rc, "dots_decode_gemm_qkv")
+    return out
+
+
+def decode_gemm_resnorm(x: torch.Tensor, w: torch.Tensor, resid: torch.Tensor, ln_w: torch.Tensor, normed: torch.Tensor, stats: torch.Tensor,
+                        counter: torch.Tensor, eps: float) -> None:
+    """o_proj / down_proj of a decode step with residual add and the next RMSNorm fused (batch <= 64):
+    resid += bf16(x @ w.T); normed = RMSNorm(resid) * ln_w.  ``counter``: one zeroed int32 (re-armed by decode_embed_rmsnorm)."""
+    _bf16_2d(x, "x"); _bf16_2d(w, "w"); _bf16_2d(resid, "resid"); _bf16_2d(normed, "normed")
+    B, Kd = x.shape
+    N = w.shape[0]
+    assert resid.shape == (B, N) and normed.shape == (B, N) and resid.is_contiguous() and normed.is_contiguous()
+    assert stats.dtype == torch.float32 and stats.numel() >= -(-N // 128) * 64 and counter.dtype == torch.int32
+    rc = _lib.load().dots_decode_gemm_resnorm(_p(x), _ll(x.stride(0)), _p(w), _ll(w.stride(0)), _p(resid), _p(ln_w), _p(normed), _p(stats),
+                                              _p(counter), B, N, Kd, C.c_float(eps), _stream())
+    _lib.check(rc, "dots_decode_gemm_resnorm")
+
+
+def decode_gemm_max_clusters(batch: int) -> int:
+    n = C.c_int(0)
+    _lib.check(_lib.load().dots_decode_gemm_max_clusters(int(batch), C.byref(n)), "dots_decode_gemm_max_clusters")
+    return int(n.value)
+
+
+def attn_decode_qkv(qkv, pos, inv_freq, k_cache, v_cache, ctx_len, out, n_q_heads: int, n_kv_heads: int, ctx_max: int, n_splits: int,
+                    scale: float, part_o=None, part_ml=None, head_dim: int = 128):
+    """RoPE + KV append + decode attention from the bf16 q|k|v row of decode_gemm_qkv."""
+    B = out.shape[0]
+    _bf16_2d(qkv, "qkv")
+    assert qkv.is_contiguous() and ctx_len.dtype == torch.int32 and pos.dtype == torch.int32
+    rc = _lib.load().dots_attn_decode_qkv(_p(qkv), _p(pos), _p(inv_freq), _p(k_cache), _p(v_cache), _p(ctx_len), _p(out), _p(part_o),
+                                          _p(part_ml), B, n_q_heads, n_kv_heads, head_dim, _ll(ctx_max), n_splits, C.c_float(scale), _stream())
+    _lib.check(rc, "dots_attn_decode_qkv")
+    return out
+
+
+ATTN_DECODE_MAX_CLUSTER = 4      # key splits the decode attention merges on chip (DEC_MAX_CLUSTER in attn_decode.cu)
+DECODE_CLUSTER = True
+
+
+def set_decode_cluster(enable: bool) -> None:
+    global DECODE_CLUSTER
+    DECODE_CLUSTER = bool(enable)
+    _lib.check(_lib.load().dots_set_decode_cluster(int(bool(enable))), "dots_set_decode_cluster")
+
+
+def debug_set_fault(code: int) -> None:
+    """Test-only fault injection (0 = off); see dots_debug_set_fault."""
+    _lib.check(_lib.load().dots_debug_set_fault(int(code)), "dots_debug_set_fault")
 
 
 def decode_residual_rmsnorm(partial, splits, resid, w, normed, eps):

@@ -110,6 +110,20 @@ DOTS_API int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, co
                            float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
                            long long ctx_max, int n_splits, float softmax_scale, void* stream);
 
+/* dots_attn_decode_fused with the current token's q|k|v as the bf16 row [batch][(n_q_heads + 2 n_kv_heads) * 128] written by
+ * dots_decode_gemm_qkv (bias already added): RoPE at pos[b] + KV append + attention. */
+DOTS_API int dots_attn_decode_qkv(const void* qkv_bf16, const int* pos, const float* inv_freq, void* k_cache, void* v_cache,
+                         const int* ctx_len, void* out, float* part_o, float* part_ml, int batch, int n_q_heads,
+                         int n_kv_heads, int head_dim, long long ctx_max, int n_splits, float softmax_scale, void* stream);
+
+/* 1 (default): 2..4 key splits of a (sequence, kv head) run as one thread-block cluster and are merged through distributed
+ * shared memory by the leader CTA (no partial buffers, no combine launch); 0: always the combine kernel. */
+DOTS_API int dots_set_decode_cluster(int enable);
+
+/* TEST ONLY: fault injection that a parity test must detect (tests/test_bench_config_gpu.py).  0 = off; 1 = the decode
+ * attention kernel drops the P*V contribution of the first 64-key tile of every sequence; 2 = of every other key tile. */
+DOTS_API int dots_debug_set_fault(int code);
+
 /* ---- HBM-bound elementwise / reduction kernels ------------------------------------------------ */
 
 /* pixel_values [rows, cols] fp32 (or bf16) -> bf16 [rows, ldo] zero-padded ([V]:586 `.to(dtype)`). */
@@ -168,14 +182,37 @@ DOTS_API int dots_argmax_advance(const void* logits, long long ldl, int batch, i
                         long long forced_ld, void* stream);
 
 /* ---- decode-step fused finalize kernels (split-K reduce + HF rounding points) ------------------ */
+/* First kernel of a decode step: resid = embed[ids]; normed = RMSNorm(resid) * w; also zeroes counters[0..n_counters) -- the
+ * rendezvous counters of this step's dots_decode_gemm_resnorm launches (counters may be NULL with n_counters == 0). */
 DOTS_API int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
-                              void* normed, int batch, int H, float eps, void* stream);
+                              void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, void* stream);
 DOTS_API int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed,
                                  int batch, int H, float eps, void* stream);
 DOTS_API int dots_decode_qkv_rope_append(const float* partial, int splits, const void* bias, const int* pos,
                                 const float* inv_freq, void* q_out, void* k_cache, void* v_cache, long long ctx_max,
                                 int batch, int n_q_heads, int n_kv_heads, int head_dim, void* stream);
 DOTS_API int dots_decode_swiglu(const float* partial, int splits, void* act, int batch, int inter, void* stream);
+
+/* ---- decode-step projections with the split-K reduction on chip (thread-block clusters + distributed shared memory) ---- */
+
+/* q|k|v projection of one decode step, batch <= 64: out[b, n] = bf16(X[b, :] . W[n, :] + bias[n])  ([Q]:217-219, fused
+ * q|k|v weight).  K is split over the 8 CTAs of a cluster per 128-row weight tile and reduced through distributed shared
+ * memory in split order (deterministic); replaces dots_gemm_skinny_bf16(partials) + the reduction in its consumer. */
+DOTS_API int dots_decode_gemm_qkv(const void* X, long long ldx, const void* W, long long ldw, const void* bias, void* out,
+                         long long ldo, int batch, int N, int K, void* stream);
+
+/* o_proj / down_proj of one decode step with everything up to the next GEMM's input fused, batch <= 64:
+ *   x = bf16(bf16(X . W^T) + resid);  resid = x;  normed = bf16(bf16(x * rsqrt(mean x^2 + eps)) * ln_w)
+ * ([Q]:243,302-308 and :46-48,308 + :258-263).  stats: scratch [ceil(N/128)][64] fp32; counter: one uint32 that is ZERO
+ * when the kernel starts (the kernel's CTAs rendezvous on it once; dots_decode_embed_rmsnorm re-zeroes a block of counters at
+ * the start of every step).  All ceil(N/128) clusters must be co-resident (checked: see dots_decode_gemm_max_clusters).
+ * Replaces dots_gemm_skinny_bf16(partials) + dots_decode_residual_rmsnorm. */
+DOTS_API int dots_decode_gemm_resnorm(const void* X, long long ldx, const void* W, long long ldw, void* resid, const void* ln_w,
+                             void* normed, float* stats, unsigned int* counter, int batch, int N, int K, float eps,
+                             void* stream);
+
+/* Number of 8-CTA clusters of dots_decode_gemm_resnorm the current device keeps resident at once. */
+DOTS_API int dots_decode_gemm_max_clusters(int batch, int* out);
 
 /* ---- CUDA-graph helpers (the decode step is captured once and replayed) ----------------------- */
 DOTS_API int dots_graph_begin(void* stream);

@@ -223,3 +223,40 @@ def test_batching_runner_matches_single_page_calls(tiny):
     br.close()
     assert out == single
     assert sum(br.batches) == len(pages) and len(br.batches) < len(pages)          # at least some calls shared a generate
+
+
+def test_parity_checks_are_sensitive_to_attention(tiny):
+    """the `peaked` id test cannot see the attention (the successor is a function of the last
+    token).  The `random`-weight checks can: with the test-only fault switch on (decode attention loses the P*V term of its
+    first 64-key tile -- at these context lengths that is every key) the teacher-forced logits criterion of
+    test_teacher_forced_logits_random fails by more than 10x and the greedy ids change, while the peaked ids do not move."""
+    from dots_ocr_b200 import ops
+    from oracle.model import DotsOracle
+    cfg, d = tiny
+    ck, eng = d["random"]
+    pv, grid, rows = _inputs(cfg, [(1, 8, 8), (1, 8, 8)])
+    ids = torch.stack(rows)
+    N = 12
+    o32 = DotsOracle(cfg, ck, torch.float32, "cpu")
+    new = o32.generate(ids, pixel_values=pv, image_grid_thw=grid, max_new_tokens=N)[:, ids.shape[1]:]
+    ref_logits = o32.teacher_forced_logits(ids, new, pv, grid)
+    sd = ref_logits.std()
+    res = {}
+    try:
+        for code in (0, 1):
+            ops.debug_set_fault(code)
+            out = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N, forced_ids=new, return_logits=True)
+            free = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N).sequences[:, ids.shape[1]:].cpu()
+            res[code] = (float((out.logits.float().cpu()[:, 1:] - ref_logits[:, 1:]).abs().max() / sd), free)
+        pk_ck, pk_eng = d["peaked"]
+        pk = {}
+        for code in (0, 1):
+            ops.debug_set_fault(code)
+            pk[code] = pk_eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N).sequences.cpu()
+    finally:
+        ops.debug_set_fault(0)
+    print(f"decode-step logits error / sigma: clean {res[0][0]:.4f}, with the fault {res[1][0]:.4f}")
+    assert res[0][0] < LOGIT_TOL_T0_FLOOR * 1.5
+    assert res[1][0] > 10 * LOGIT_TOL_T1, res[1][0]
+    assert not torch.equal(res[0][1], res[1][1]), "greedy ids on random weights must react to broken attention"
+    assert torch.equal(pk[0], pk[1])      # ... which is exactly why the peaked id test is plumbing only

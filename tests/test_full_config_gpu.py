@@ -57,8 +57,10 @@ def test_full_size_single_page_matches_hf_bf16():
     assert torch.equal(got_ids, ref_ids), (got_ids[0, -N:].tolist(), ref_ids[0, -N:].tolist())
 
 
-def test_full_size_logits_random_weights():
-    """Pre-sampling logits at the real dimensions, N(0, 0.02) weights (no peaked head), teacher-forced on the oracle's ids.
+@pytest.mark.parametrize("side", [1024, 1960])
+def test_full_size_logits_random_weights(side):
+    """side = 1960: BASELINE configs[4]'s page (19 600 ViT tokens, 4 900 image tokens, T = 4 964) end to end against the oracle.
+    Pre-sampling logits at the real dimensions, N(0, 0.02) weights (no peaked head), teacher-forced on the oracle's ids.
     70 bf16 layers deep, two correct bf16 pipelines differ by more than the 0.06 sigma seen on the 2-layer config, so the
     criterion is relative: the engine's error against the fp32 oracle (same weights, fp32 arithmetic on the GPU) must be no
     worse than 1.5 x the error HF's own bf16 forward shows against it (floor 0.06 sigma)."""
@@ -68,8 +70,9 @@ def test_full_size_logits_random_weights():
     from oracle.model import DotsOracle
     cfg = config.full()
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=DEV)
-    gh, gw = vit_grid(1024, 1024)
-    s_vit, t_img = token_counts(1024, 1024, patch=cfg.vision.patch_size, merge=cfg.vision.spatial_merge_size)
+    gh, gw = vit_grid(side, side)
+    s_vit, t_img = token_counts(side, side, patch=cfg.vision.patch_size, merge=cfg.vision.spatial_merge_size)
+    assert side != 1960 or (s_vit, t_img) == (19600, 4900)
     g = torch.Generator().manual_seed(99)
     pv = torch.randn(s_vit, cfg.vision.patch_dim, generator=g)
     grid = torch.tensor([[1, gh, gw]])
@@ -80,15 +83,22 @@ def test_full_size_logits_random_weights():
     ref_ids = orc.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N).cpu()
     new = ref_ids[:, ids.shape[1]:]
     ref16 = orc.teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()               # [1, N, V]
+    img16 = orc.vision.forward(pv.to(DEV), grid).float().cpu()
     del orc
     torch.cuda.empty_cache()
     orc32 = DotsOracle(cfg, ck, torch.float32, DEV)
     ref32 = orc32.teacher_forced_logits(ids, new, pv.to(DEV), grid).cpu()
+    img32 = orc32.vision.forward(pv.to(DEV), grid).float().cpu()
     del orc32
     torch.cuda.empty_cache()
     eng = Engine(cfg, ck, DEV)
     out = eng.generate(ids, pixel_values=pv.to(DEV), image_grid_thw=grid, max_new_tokens=N, forced_ids=new, return_logits=True)
     got = out.logits.float().cpu()
+    img = out.image_embeds.float().cpu()
+    rms = float(img32.pow(2).mean().sqrt())
+    img_eng, img_hf = float((img - img32).pow(2).mean().sqrt()) / rms, float((img16 - img32).pow(2).mean().sqrt()) / rms
+    print(f"{side}x{side} image embeds, rms error vs fp32: engine {img_eng:.3e}, bf16 oracle {img_hf:.3e}")
+    assert img.shape == (t_img, cfg.text.hidden_size) and img_eng < max(1.5 * img_hf, 1e-2), (img_eng, img_hf)
     sd = float(ref32.std())
     err_eng = float((got - ref32).abs().max()) / sd
     err_hf = float((ref16 - ref32).abs().max()) / sd
