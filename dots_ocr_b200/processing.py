@@ -121,7 +121,9 @@ class HFTokenizer:
     def __init__(self, path_or_tokenizer, image_token_id: Optional[int] = None, generation_config: Optional[dict] = None):
         if isinstance(path_or_tokenizer, str):
             from transformers import AutoTokenizer
-            tok = AutoTokenizer.from_pretrained(path_or_tokenizer)
+            # the published checkpoint ships its own configuration / processor classes and the reference loads it with
+            # trust_remote_code=True (dots_ocr/parser.py:68-75); without it transformers stops at an interactive prompt
+            tok = AutoTokenizer.from_pretrained(path_or_tokenizer, trust_remote_code=True)
             if generation_config is None:
                 import json
                 import os

@@ -63,6 +63,9 @@ def hf_config_dict(cfg) -> dict:
     sp = special_token_ids(cfg)
     return dict(
         architectures=["DotsOCRForCausalLM"], model_type="dots_ocr", torch_dtype="bfloat16",
+        # like the published checkpoint, the directory carries its own configuration class (trust_remote_code): transformers and
+        # vLLM 0.22 know no built-in `dots_ocr` model type; the class re-exports vLLM's DotsOCRConfig when vLLM is importable
+        auto_map={"AutoConfig": "configuration_dots.DotsOCRConfig"},
         hidden_size=t.hidden_size, intermediate_size=t.intermediate_size, num_hidden_layers=t.num_hidden_layers,
         num_attention_heads=t.num_attention_heads, num_key_value_heads=t.num_key_value_heads, vocab_size=t.vocab_size,
         rms_norm_eps=t.rms_norm_eps, rope_theta=t.rope_theta, max_position_embeddings=t.max_position_embeddings,
@@ -103,12 +106,29 @@ def write_tokenizer(cfg, out: str):
     return fast
 
 
+REMOTE_CONFIG = '''"""Configuration class shipped with the checkpoint directory (config.json: auto_map, trust_remote_code=True)."""
+try:
+    from vllm.transformers_utils.configs.dotsocr import DotsOCRConfig, DotsVisionConfig      # noqa: F401
+except Exception:                                                                            # no vLLM: a plain Qwen2 config with the extra keys
+    from transformers import Qwen2Config
+
+    class DotsOCRConfig(Qwen2Config):
+        model_type = "dots_ocr"
+
+        def __init__(self, image_token_id=151665, video_token_id=151656, vision_config=None, **kw):
+            super().__init__(**kw)
+            self.image_token_id, self.video_token_id, self.vision_config = image_token_id, video_token_id, vision_config or {}
+'''
+
+
 def write_dir(cfg, out: str, seed: int = 0, flavour: str = "random", shards: int = 2) -> dict:
     from dots_ocr_b200 import weights as W
     os.makedirs(out, exist_ok=True)
     sp = special_token_ids(cfg)
     with open(os.path.join(out, "config.json"), "w") as f:
         json.dump(hf_config_dict(cfg), f, indent=2)
+    with open(os.path.join(out, "configuration_dots.py"), "w") as f:
+        f.write(REMOTE_CONFIG)
     with open(os.path.join(out, "generation_config.json"), "w") as f:
         json.dump({"do_sample": False, "eos_token_id": [sp["<|endoftext|>"], sp["<|endofassistant|>"]],
                    "pad_token_id": sp["<|endoftext|>"], "max_new_tokens": 24000}, f, indent=2)

@@ -69,6 +69,49 @@ __global__ void stream_kernel(const uint8_t* __restrict__ src, size_t bytes_per_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ stream through 2-D tensor maps
+// Same ring, but every box is a cp.async.bulk.tensor.2d of [box_rows x 64 bf16] (128-byte rows, 128-B swizzle) -- the shape every
+// weight / KV tile of the decode kernels has.  pitch_elems = 64: the box rows are contiguous in memory (16 KB blob);
+// pitch_elems = 1536: rows 3072 B apart (a K-major weight matrix).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__global__ void stream2d_kernel(const __grid_constant__ CUtensorMap tm, int boxes_per_cta, int stages, int box_rows, int kblocks, unsigned* sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 32;
+    uint8_t* ring = smem + 1024;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int box = box_rows * 128;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < boxes_per_cta; ++i) {
+                const int st = i % stages;
+                if (i >= stages) mbar_wait(&empty[st], ((i / stages) & 1) ^ 1);
+                mbar_expect_tx(&full[st], box);
+                const long long g = (long long)blockIdx.x * boxes_per_cta + i;        // global box index: row tile = g / kblocks, k-block = g % kblocks
+                tma_load_2d(ring + (size_t)st * box, &tm, (int)(g % kblocks) * 64, (int)(g / kblocks) * box_rows, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        unsigned acc = 0;
+        for (int i = 0; i < boxes_per_cta; ++i) {
+            const int st = i % stages;
+            mbar_wait(&full[st], (i / stages) & 1);
+            acc += *reinterpret_cast<const volatile unsigned*>(ring + (size_t)st * box + lane * 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        if (acc == 0x12345678u) sink[0] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pdl chain
 // Kernel i: wait for kernel i-1, read what it wrote (148 x 128 floats), add 1, write.  A real producer/consumer boundary.
 __global__ void chain_kernel(const float* __restrict__ in, float* __restrict__ out, int use_pdl) {
@@ -152,14 +195,15 @@ static float time_graph(cudaGraphExec_t g, cudaStream_t st, int reps) {
     return ms / reps;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool quick = argc > 1;       // any argument: skip the long 1-D sweep
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
     cudaStream_t st; CK(cudaStreamCreate(&st));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 
     // ---- stream: 8 GB buffer (>> L2), each config reads ~4 GB
-    {
+    if (!quick) {
         const size_t total = (size_t)8 << 30;
         uint8_t* src; CK(cudaMalloc(&src, total)); CK(cudaMemset(src, 1, total));
         unsigned* sink; CK(cudaMalloc(&sink, 4));
@@ -200,6 +244,55 @@ int main() {
             CK(cudaStreamSynchronize(st));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
             printf("{\"k\": \"stream_sms\", \"ctas\": %d, \"box\": %d, \"stages\": %d, \"gbs\": %.0f}\n", g, box, stages, (double)per_cta * g / ms / 1e6);
+        }
+        CK(cudaFree(src)); CK(cudaFree(sink));
+    }
+
+    // ---- 2-D tensor-map streaming: [rows, pitch] bf16, boxes of box_rows x 64 elements (128-B rows)
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+        EncodeFn enc = (EncodeFn)fp;
+        const size_t total = (size_t)6 << 30;
+        uint8_t* src; CK(cudaMalloc(&src, total)); CK(cudaMemset(src, 1, total));
+        unsigned* sink; CK(cudaMalloc(&sink, 4));
+        CK(cudaFuncSetAttribute(stream2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        const int pitches[] = {64, 1536, 8960};
+        for (int pitch : pitches) {
+            for (int box_rows : {64, 128}) {
+                for (int swz = 0; swz < 2; ++swz) {
+                    const cuuint64_t cols = pitch, rows = total / 2 / pitch;
+                    cuuint64_t gdim[2] = {cols, rows}; cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2};
+                    cuuint32_t bx[2] = {64, (cuuint32_t)box_rows}; cuuint32_t es[2] = {1, 1};
+                    CUtensorMap tm;
+                    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, src, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) { printf("{\"k\": \"stream2d\", \"error\": %d}\n", (int)r); continue; }
+                    const int kblocks = pitch / 64;
+                    for (int per_sm = 1; per_sm <= 2; ++per_sm) {
+                        for (int stages : {4, 8}) {
+                            const int box = box_rows * 128;
+                            size_t smem = 1024 + (size_t)stages * box;
+                            const size_t floor_ = (size_t)(227 * 1024) / (per_sm + 1) + 1024;
+                            if (smem < floor_) smem = floor_;
+                            if (smem * per_sm > 224 * 1024) continue;
+                            const int grid = sms * per_sm;
+                            const int boxes_per_cta = (int)(((size_t)3 << 30) / grid / box);
+                            stream2d_kernel<<<grid, 64, smem, st>>>(tm, boxes_per_cta, stages, box_rows, kblocks, sink);
+                            CK(cudaEventRecord(e0, st));
+                            stream2d_kernel<<<grid, 64, smem, st>>>(tm, boxes_per_cta, stages, box_rows, kblocks, sink);
+                            CK(cudaEventRecord(e1, st));
+                            CK(cudaStreamSynchronize(st));
+                            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                            printf("{\"k\": \"stream2d\", \"pitch_elems\": %d, \"box_rows\": %d, \"swizzle128\": %d, \"ctas_per_sm\": %d, \"stages\": %d, \"gbs\": %.0f}\n",
+                                   pitch, box_rows, swz, per_sm, stages, (double)boxes_per_cta * box * grid / ms / 1e6);
+                            fflush(stdout);
+                        }
+                    }
+                }
+            }
         }
         CK(cudaFree(src)); CK(cudaFree(sink));
     }

@@ -43,7 +43,7 @@ def run_vllm(a) -> dict:
     from vllm import LLM, SamplingParams
     from dots_ocr_b200.processing import HFTokenizer
     text = HFTokenizer(a.dir).render(PROMPT)                     # ...<|img|><|imgpad|><|endofimg|>{prompt}...; vLLM widens the pad
-    llm = LLM(model=a.dir, tokenizer=a.dir, dtype="bfloat16", max_model_len=a.max_model_len, max_num_seqs=a.pages,
+    llm = LLM(model=a.dir, tokenizer=a.dir, dtype="bfloat16", trust_remote_code=True, max_model_len=a.max_model_len, max_num_seqs=a.pages,
               limit_mm_per_prompt={"image": 1}, gpu_memory_utilization=a.gpu_mem, enable_prefix_caching=False,
               enforce_eager=a.eager)
     sp = SamplingParams(temperature=0.0, max_tokens=a.new_tokens, ignore_eos=True, detokenize=False)
