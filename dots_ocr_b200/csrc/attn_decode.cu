@@ -56,6 +56,7 @@ struct DecParams {
     const float* qkv_partial;
     const bf16* qkv_bf16;     // [B][(nq + 2 nkv) * 128], bias already added (dots_decode_gemm_qkv); alternative to qkv_partial
     int qkv_splits;
+    int out_tile_rows;        // > 0: `out` is written in the k-block-tiled activation layout with this many rows per tile
     int cluster_merge;        // 1: the n_splits CTAs of a (sequence, kv head) are one cluster and merge through DSMEM
     int fault;                // test-only fault injection (dots_debug_set_fault): 1 = key tile 0, 2 = every other key tile loses its P*V term
     const bf16* qkv_bias;
@@ -83,8 +84,13 @@ __device__ __forceinline__ uint32_t dec_tile_off(int row, int chunk) {
     return (uint32_t)((chunk >> 3) * DEC_BOX_BYTES + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
 }
 
+// element offset of out[b][col]: row-major [B, n_q_heads * 128], or (out_tile_rows > 0) the k-block-tiled B operand of o_proj
+__device__ __forceinline__ long long dec_out_off(const DecParams& p, int b, int col) {
+    return p.out_tile_rows > 0 ? tiled_row_off(b, col, p.out_tile_rows) : (long long)b * p.n_q_heads * DEC_D + col;
+}
+
 __global__ void __launch_bounds__(DEC_THREADS)
-attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const DecParams p) {
+attn_decode_kernel(const DecParams p) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,7 +112,11 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     const int k_begin = split * chunk;
     const int k_end = min(ctx, k_begin + chunk);
     const int n_tiles = (k_end > k_begin) ? (k_end - k_begin + DEC_RING_KEYS - 1) / DEC_RING_KEYS : 0;
-    const int row0 = (b * p.n_kv_heads + kvh) * (int)p.ctx_max + k_begin;       // tensor-map row of this CTA's first key
+    // The cache stripe of (sequence, kv head) is stored in 64-key tiles of 16 KB that already hold the shared-memory image this
+    // kernel wants ([dims 0-63 | dims 64-127][64 keys], 128-B rows swizzled): one 1-D bulk copy per K tile and per V tile.
+    const long long stripe = ((long long)b * p.n_kv_heads + kvh) * p.ctx_max * DEC_D;
+    const bf16* k_src = p.kc + stripe + (long long)k_begin * DEC_D;           // k_begin is a multiple of 64: tile aligned
+    const bf16* v_src = p.vc + stripe + (long long)k_begin * DEC_D;
     // the split whose key range holds key ctx-1, the token appended this step (its cache row is written by this kernel's
     // fused QKV finalize, or by the predecessor kernel on the unfused path)
     const bool holds_new = (ctx - 1 >= k_begin) && (ctx - 1 < k_end);
@@ -127,14 +137,11 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
             const int st = i % DEC_STAGES;
             uint8_t* dst = ring + st * DEC_STAGE_BYTES;
             mbar_expect_tx(&full_bar[st], DEC_STAGE_BYTES);
-            tma_load_2d(dst, &tm_k, 0, row0 + i * DEC_RING_KEYS, &full_bar[st]);
-            tma_load_2d(dst + DEC_BOX_BYTES, &tm_k, 64, row0 + i * DEC_RING_KEYS, &full_bar[st]);
-            tma_load_2d(dst + 2 * DEC_BOX_BYTES, &tm_v, 0, row0 + i * DEC_RING_KEYS, &full_bar[st]);
-            tma_load_2d(dst + 3 * DEC_BOX_BYTES, &tm_v, 64, row0 + i * DEC_RING_KEYS, &full_bar[st]);
+            bulk_load(dst, k_src + (long long)i * DEC_RING_KEYS * DEC_D, 2 * DEC_BOX_BYTES, &full_bar[st]);
+            bulk_load(dst + 2 * DEC_BOX_BYTES, v_src + (long long)i * DEC_RING_KEYS * DEC_D, 2 * DEC_BOX_BYTES, &full_bar[st]);
         };
         int i = 0;
         if (lane == 0) {
-            prefetch_tensormap(&tm_k); prefetch_tensormap(&tm_v);
             for (; i < early && i < DEC_STAGES; ++i) issue(i);          // ring-full of immutable tiles ahead of the wait
         }
         __syncwarp();
@@ -233,9 +240,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
                 *reinterpret_cast<uint2*>(sQ + swz128(hl, c4 >> 1) + (c4 & 1) * 8) = r1;
                 *reinterpret_cast<uint2*>(sQ + swz128(hl, 8 + (c4 >> 1)) + (c4 & 1) * 8) = r2;
             } else {
-                bf16* dst = (hl == p.group ? p.kc_w : p.vc_w) + (((long long)b * p.n_kv_heads + kvh) * p.ctx_max + posb) * DEC_D + c4 * 4;
-                *reinterpret_cast<uint2*>(dst) = r1;
-                *reinterpret_cast<uint2*>(dst + 64) = r2;
+                bf16* dst = (hl == p.group ? p.kc_w : p.vc_w) + stripe;
+                *reinterpret_cast<uint2*>(dst + kv_tiled_off(posb, c4 * 4)) = r1;
+                *reinterpret_cast<uint2*>(dst + kv_tiled_off(posb, 64 + c4 * 4)) = r2;
             }
         }
     }
@@ -385,7 +392,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 #pragma unroll
         for (int r = 0; r < 8; ++r)
             if (r < p.group)
-                p.out[((long long)b * p.n_q_heads + kvh * p.group + r) * DEC_D + c] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
+                p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
     } else if (p.cluster_merge) {
         // ---- on-chip merge across the cluster: peers write (O, m, l) into the leader's shared memory, the leader combines
         //      in split order (same arithmetic as attn_decode_combine_kernel) ----
@@ -424,7 +431,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
                     acc += w * pm[r * DEC_D + c];
                     l += w * pm[8 * DEC_D + r * 2 + 1];
                 }
-                p.out[((long long)b * p.n_q_heads + kvh * p.group + r) * DEC_D + c] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+                p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
             }
         }
     } else {
@@ -440,7 +447,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 
 __global__ void __launch_bounds__(DEC_D)
 attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ out,
-                           int n_splits) {
+                           int n_splits, int n_q_heads, int out_tile_rows) {
     pdl_wait();
     pdl_launch_dependents();
     const long long bh = blockIdx.x;          // b * n_q_heads + head
@@ -454,7 +461,8 @@ attn_decode_combine_kernel(const float* __restrict__ part_o, const float* __rest
         acc += w * part_o[(bh * n_splits + s) * DEC_D + c];
         l += w * part_ml[(bh * n_splits + s) * 2 + 1];
     }
-    out[bh * DEC_D + c] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+    const int b = (int)(bh / n_q_heads), col = (int)(bh % n_q_heads) * DEC_D + c;
+    out[out_tile_rows > 0 ? tiled_row_off(b, col, out_tile_rows) : bh * DEC_D + c] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
 }
 
 }  // namespace dots
@@ -484,21 +492,17 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              DEC_SMEM + (DEC_MAX_CLUSTER - 1) * DEC_MERGE_BYTES));
     }
-    // K / V cache layer slice [batch * n_kv_heads * ctx_max, 128] bf16, fetched as [64 keys][64 dims] 128-B-swizzled boxes
-    const unsigned long long rows = (unsigned long long)batch * n_kv_heads * (unsigned long long)p.ctx_max;
-    DOTS_REQUIRE(rows < (1ull << 31), "%s: cache too large for 32-bit key coordinates", who);
-    CUtensorMap tk, tv;
-    if (make_tmap_2d_bf16(&tk, p.kc, rows, DEC_D, DEC_D, DEC_RING_KEYS, 64)) return -4;
-    if (make_tmap_2d_bf16(&tv, p.vc, rows, DEC_D, DEC_D, DEC_RING_KEYS, 64)) return -4;
+    DOTS_REQUIRE(p.ctx_max % DEC_RING_KEYS == 0, "%s: ctx_max must be a multiple of %d (the cache is stored in 64-key tiles)", who, DEC_RING_KEYS);
+    DOTS_REQUIRE(p.out_tile_rows == 0 || (p.out_tile_rows % 8 == 0 && batch <= p.out_tile_rows), "%s: bad out_tile_rows %d", who, p.out_tile_rows);
     dim3 grid(n_splits, n_kv_heads, batch);
     if (cluster) {
         DOTS_CHECK_CUDA(launch_ex_cluster(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM + (n_splits - 1) * DEC_MERGE_BYTES), st,
-                                          true, (unsigned)n_splits, tk, tv, p));
+                                          true, (unsigned)n_splits, p));
         return 0;
     }
-    DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, tk, tv, p));
+    DOTS_CHECK_CUDA(launch_ex(attn_decode_kernel, dim3(grid), dim3(DEC_THREADS), (size_t)(DEC_SMEM), st, true, p));
     if (n_splits > 1) {
-        DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, p.part_o, p.part_ml, p.out, n_splits));
+        DOTS_CHECK_CUDA(launch_ex(attn_decode_combine_kernel, dim3(batch * n_q_heads), dim3(DEC_D), (size_t)(0), st, true, p.part_o, p.part_ml, p.out, n_splits, n_q_heads, p.out_tile_rows));
     }
     return 0;
 }
@@ -528,10 +532,11 @@ extern "C" int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, 
 // Same as dots_attn_decode_fused, with q|k|v of the current token arriving as the bf16 row [batch][(nq + 2 nkv) * 128] that
 // dots_decode_gemm_qkv wrote (bias already added): RoPE + KV append + attention.
 extern "C" int dots_attn_decode_qkv(const void* qkv_bf16, const int* pos, const float* inv_freq, void* k_cache, void* v_cache, const int* ctx_len,
-                                    void* out, float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
-                                    long long ctx_max, int n_splits, float softmax_scale, void* stream) {
+                                    void* out, int out_tile_rows, float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads,
+                                    int head_dim, long long ctx_max, int n_splits, float softmax_scale, void* stream) {
     DOTS_REQUIRE(qkv_bf16 && pos && inv_freq, "dots_attn_decode_qkv: missing QKV inputs");
     DecParams p{};
+    p.out_tile_rows = out_tile_rows;
     p.q = nullptr; p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.ctx_len = ctx_len;
     p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
     p.qkv_bf16 = (const bf16*)qkv_bf16; p.pos = pos; p.inv_freq = inv_freq;

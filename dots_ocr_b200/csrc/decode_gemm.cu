@@ -36,6 +36,8 @@ constexpr int DG_MODE_QKV = 0;
 constexpr int DG_MODE_RESNORM = 1;
 
 struct DgParams {
+    const uint8_t* w_tiled;  // weights as [ceil(N/128)][ceil(K/64)] blobs of 16 KB (ops.tile_weight): one bulk copy per ring stage
+    const uint8_t* x_tiled;  // activations as [ceil(K/64)] blobs of BN x 128 B (ops.tile_rows with BN rows per tile)
     int N, K, batch;
     int num_k_blocks, kb_per_split;
     const bf16* bias;        // QKV
@@ -43,7 +45,7 @@ struct DgParams {
     long long ldo;
     bf16* resid;             // RESNORM: [batch, N] in/out
     const bf16* ln_w;        // RESNORM: weight of the RMSNorm that follows
-    bf16* normed;            // RESNORM: [batch, N]
+    bf16* normed;            // RESNORM: normalised activations in the k-block-tiled layout, BN rows per tile (next GEMM's B operand)
     float* stats;            // RESNORM: [n_tiles][64] sums of squares
     unsigned* counter;       // RESNORM: CTAs of this launch that have published their statistics
     float eps;
@@ -69,7 +71,7 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, f
 
 template <int BN, int CS, int MODE>
 __global__ void __launch_bounds__(DG_THREADS, 1)
-decode_gemm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const DgParams p) {
+decode_gemm_cluster_kernel(const DgParams p) {
     using S = DgSmem<BN, CS>;
     constexpr int COLS = S::COLS;
     extern __shared__ uint8_t smem_raw[];
@@ -91,7 +93,6 @@ decode_gemm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
     const int nk = max(0, kb1 - kb0);               // an empty split contributes zeros
 
-    if (warp == 0 && lane == 0) { prefetch_tensormap(&tmap_w); prefetch_tensormap(&tmap_x); }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < DG_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(tmem_full, 1);
@@ -112,10 +113,12 @@ decode_gemm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         // ===================== TMA producer =====================
         if (lane == 0) {
             // weights never depend on a predecessor kernel: the first ring-full is requested before the dependency wait
+            const uint8_t* wsrc = p.w_tiled + ((size_t)tile * p.num_k_blocks + kb0) * S::A_BYTES;      // this CTA's k-blocks are contiguous
+            const uint8_t* xsrc = p.x_tiled + (size_t)kb0 * S::B_BYTES;
             const int pre = min(nk, DG_STAGES);
             for (int i = 0; i < pre; ++i) {
                 mbar_expect_tx(&full_bar[i], S::STAGE_BYTES);
-                tma_load_2d(smem_a + i * S::A_BYTES, &tmap_w, (kb0 + i) * DG_BK, tile * DG_BM, &full_bar[i]);
+                bulk_load(smem_a + i * S::A_BYTES, wsrc + (size_t)i * S::A_BYTES, S::A_BYTES, &full_bar[i]);
             }
             pdl_wait();
             int stage = 0;
@@ -124,9 +127,9 @@ decode_gemm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
                 if (i >= pre) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_w, (kb0 + i) * DG_BK, tile * DG_BM, &full_bar[stage]);
+                    bulk_load(smem_a + stage * S::A_BYTES, wsrc + (size_t)i * S::A_BYTES, S::A_BYTES, &full_bar[stage]);
                 }
-                tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_x, (kb0 + i) * DG_BK, 0, &full_bar[stage]);
+                bulk_load(smem_b + stage * S::B_BYTES, xsrc + (size_t)i * S::B_BYTES, S::B_BYTES, &full_bar[stage]);
                 if (++stage == DG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -258,7 +261,7 @@ decode_gemm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
 #pragma unroll
             for (int j = 0; j < COLS; ++j)
                 if (feat_ok && b0 + j < p.batch)
-                    p.normed[(long long)(b0 + j) * p.N + feat] = __float2bfloat16_rn(bf16_round(x[j] * s_red[4 * COLS + j]) * w);
+                    p.normed[tiled_row_off(b0 + j, feat, BN)] = __float2bfloat16_rn(bf16_round(x[j] * s_red[4 * COLS + j]) * w);
         }
     }
 
@@ -271,14 +274,14 @@ decode_gemm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
 }
 
 template <int BN, int CS, int MODE>
-static int launch_decode_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const DgParams& p, int n_tiles, cudaStream_t st) {
+static int launch_decode_gemm(const DgParams& p, int n_tiles, cudaStream_t st) {
     using S = DgSmem<BN, CS>;
     auto kern = decode_gemm_cluster_kernel<BN, CS, MODE>;
     static bool configured[64] = {false};
     if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     }
-    DOTS_CHECK_CUDA(launch_ex_cluster(kern, dim3(CS, n_tiles), dim3(DG_THREADS), (size_t)S::TOTAL, st, true, (unsigned)CS, tw, tx, p));
+    DOTS_CHECK_CUDA(launch_ex_cluster(kern, dim3(CS, n_tiles), dim3(DG_THREADS), (size_t)S::TOTAL, st, true, (unsigned)CS, p));
     return 0;
 }
 
@@ -301,16 +304,15 @@ static int max_clusters_resnorm(int* out) {
 
 constexpr int DG_CS = 8;       // portable cluster size; two clusters of 8 fit one GPC (>= 16 SMs) -> >= 16 co-resident clusters
 
-static int prep(DgParams& p, CUtensorMap& tw, CUtensorMap& tx, const void* X, long long ldx, const void* W, long long ldw, int batch,
-                int N, int K, int& bn, const char* who) {
+static int prep(DgParams& p, const void* Xt, const void* Wt, int batch, int N, int K, int& bn, const char* who) {
     DOTS_REQUIRE(batch > 0 && batch <= 64 && N > 0 && K > 0, "%s: batch must be 1..64 (got %d), N=%d K=%d", who, batch, N, K);
-    DOTS_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "%s: K and pitches must be multiples of 8", who);
+    DOTS_REQUIRE((reinterpret_cast<uintptr_t>(Xt) | reinterpret_cast<uintptr_t>(Wt)) % 16 == 0, "%s: tiled operands must be 16-byte aligned", who);
+    p.w_tiled = reinterpret_cast<const uint8_t*>(Wt);
+    p.x_tiled = reinterpret_cast<const uint8_t*>(Xt);
     p.N = N; p.K = K; p.batch = batch;
     p.num_k_blocks = (K + DG_BK - 1) / DG_BK;
     p.kb_per_split = (p.num_k_blocks + DG_CS - 1) / DG_CS;
     bn = batch <= 32 ? 32 : 64;
-    if (make_tmap_2d_bf16(&tw, W, N, K, ldw, DG_BM)) return -4;
-    if (make_tmap_2d_bf16(&tx, X, batch, K, ldx, bn)) return -4;
     return 0;
 }
 
@@ -318,31 +320,32 @@ static int prep(DgParams& p, CUtensorMap& tw, CUtensorMap& tx, const void* X, lo
 
 using namespace dots;
 
-extern "C" int dots_decode_gemm_qkv(const void* X, long long ldx, const void* W, long long ldw, const void* bias, void* out, long long ldo,
-                                    int batch, int N, int K, void* stream) {
-    DOTS_REQUIRE(X && W && out, "dots_decode_gemm_qkv: null pointer");
+// Operand layouts of both entry points: Wt = ops.tile_weight(W) ([ceil(N/128)][ceil(K/64)] blobs of 16 KB), Xt = activations in the
+// k-block-tiled layout with 32 (batch <= 32) or 64 rows per tile (ops.tile_rows / tiled_row_off); both are fetched with 1-D bulk copies.
+extern "C" int dots_decode_gemm_qkv(const void* Xt, const void* Wt, const void* bias, void* out, long long ldo, int batch, int N, int K,
+                                    void* stream) {
+    DOTS_REQUIRE(Xt && Wt && out, "dots_decode_gemm_qkv: null pointer");
     DgParams p{};
-    CUtensorMap tw, tx;
     int bn = 0;
-    if (int rc = prep(p, tw, tx, X, ldx, W, ldw, batch, N, K, bn, "dots_decode_gemm_qkv")) return rc;
+    if (int rc = prep(p, Xt, Wt, batch, N, K, bn, "dots_decode_gemm_qkv")) return rc;
     p.bias = reinterpret_cast<const bf16*>(bias);
     p.out = reinterpret_cast<bf16*>(out);
     p.ldo = ldo;
     const int n_tiles = (N + DG_BM - 1) / DG_BM;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return bn == 32 ? launch_decode_gemm<32, DG_CS, DG_MODE_QKV>(tw, tx, p, n_tiles, st) : launch_decode_gemm<64, DG_CS, DG_MODE_QKV>(tw, tx, p, n_tiles, st);
+    return bn == 32 ? launch_decode_gemm<32, DG_CS, DG_MODE_QKV>(p, n_tiles, st) : launch_decode_gemm<64, DG_CS, DG_MODE_QKV>(p, n_tiles, st);
 }
 
-extern "C" int dots_decode_gemm_resnorm(const void* X, long long ldx, const void* W, long long ldw, void* resid, const void* ln_w, void* normed,
-                                        float* stats, unsigned int* counter, int batch, int N, int K, float eps, void* stream) {
-    DOTS_REQUIRE(X && W && resid && ln_w && normed && stats && counter, "dots_decode_gemm_resnorm: null pointer");
+extern "C" int dots_decode_gemm_resnorm(const void* Xt, const void* Wt, void* resid, const void* ln_w, void* normed_t, float* stats,
+                                        unsigned int* counter, int batch, int N, int K, float eps, void* stream) {
+    DOTS_REQUIRE(Xt && Wt && resid && ln_w && normed_t && stats && counter, "dots_decode_gemm_resnorm: null pointer");
+    DOTS_REQUIRE(N % 64 == 0, "dots_decode_gemm_resnorm: N must be a multiple of 64 (tiled output)");
     DgParams p{};
-    CUtensorMap tw, tx;
     int bn = 0;
-    if (int rc = prep(p, tw, tx, X, ldx, W, ldw, batch, N, K, bn, "dots_decode_gemm_resnorm")) return rc;
+    if (int rc = prep(p, Xt, Wt, batch, N, K, bn, "dots_decode_gemm_resnorm")) return rc;
     p.resid = reinterpret_cast<bf16*>(resid);
     p.ln_w = reinterpret_cast<const bf16*>(ln_w);
-    p.normed = reinterpret_cast<bf16*>(normed);
+    p.normed = reinterpret_cast<bf16*>(normed_t);
     p.stats = stats; p.counter = counter; p.eps = eps;
     const int n_tiles = (N + DG_BM - 1) / DG_BM;
     // every cluster of the launch must be resident at once (the epilogue waits on a device-wide counter)
@@ -358,8 +361,7 @@ extern "C" int dots_decode_gemm_resnorm(const void* X, long long ldx, const void
     DOTS_REQUIRE(cached >= n_tiles, "dots_decode_gemm_resnorm: %d row tiles need %d co-resident clusters of %d, the device holds %d", n_tiles,
                  n_tiles, DG_CS, cached);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return bn == 32 ? launch_decode_gemm<32, DG_CS, DG_MODE_RESNORM>(tw, tx, p, n_tiles, st)
-                    : launch_decode_gemm<64, DG_CS, DG_MODE_RESNORM>(tw, tx, p, n_tiles, st);
+    return bn == 32 ? launch_decode_gemm<32, DG_CS, DG_MODE_RESNORM>(p, n_tiles, st) : launch_decode_gemm<64, DG_CS, DG_MODE_RESNORM>(p, n_tiles, st);
 }
 
 extern "C" int dots_decode_gemm_max_clusters(int batch, int* out) {

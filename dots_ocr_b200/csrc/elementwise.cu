@@ -273,14 +273,15 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int
         *reinterpret_cast<uint4*>(base) = r1;
         *reinterpret_cast<uint4*>(base + 64) = r2;
         if (head >= nq) {
-            bf16* dst = kc + (((long long)seq_of_tok[tkn] * nkv + (head - nq)) * ctx_max + p) * 128 + c8 * 8;
-            *reinterpret_cast<uint4*>(dst) = r1;
-            *reinterpret_cast<uint4*>(dst + 64) = r2;
+            // cache stripes are stored in 64-key tiles with the shared-memory image of the decode kernel (kv_tiled_off)
+            bf16* stripe = kc + ((long long)seq_of_tok[tkn] * nkv + (head - nq)) * ctx_max * 128;
+            *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, c8 * 8)) = r1;
+            *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, 64 + c8 * 8)) = r2;
         }
     } else {
-        bf16* dst = vc + (((long long)seq_of_tok[tkn] * nkv + (head - nq - nkv)) * ctx_max + p) * 128 + c8 * 8;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(base);
-        *reinterpret_cast<uint4*>(dst + 64) = *reinterpret_cast<uint4*>(base + 64);
+        bf16* stripe = vc + ((long long)seq_of_tok[tkn] * nkv + (head - nq - nkv)) * ctx_max * 128;
+        *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, c8 * 8)) = *reinterpret_cast<uint4*>(base);
+        *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, 64 + c8 * 8)) = *reinterpret_cast<uint4*>(base + 64);
     }
 }
 
@@ -454,7 +455,7 @@ __device__ __forceinline__ void sum_splits8(const float* __restrict__ p0, long l
 __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table,
                                                                    long long vocab, const bf16* __restrict__ w, bf16* __restrict__ resid,
                                                                    bf16* __restrict__ normed, int B, int H, float eps,
-                                                                   unsigned* __restrict__ counters, int n_counters) {
+                                                                   unsigned* __restrict__ counters, int n_counters, int tile_rows) {
     pdl_wait();
     pdl_launch_dependents();
     // first kernel of a decode step: re-arm the rendezvous counters of this step's dots_decode_gemm_resnorm launches
@@ -491,7 +492,9 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
             unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] * r) * g[j];
-            reinterpret_cast<uint4*>(normed + (long long)b * H)[c] = pack8(f);
+            // tile_rows > 0: `normed` is the k-block-tiled B operand of the cluster GEMMs (tiled_row_off), else row-major
+            bf16* dst = tile_rows > 0 ? normed + tiled_row_off(b, c * 8, tile_rows) : normed + (long long)b * H + c * 8;
+            *reinterpret_cast<uint4*>(dst) = pack8(f);
         }
     }
 }
@@ -566,14 +569,19 @@ __global__ void decode_qkv_rope_append_kernel(const float* __restrict__ partial,
     if (head < nq + nkv) {
         float o1[8], o2[8];
         rope_bf16_8(x1, x2, p, inv_freq, c8 * 8, o1, o2);
-        bf16* dst = (head < nq) ? q_out + ((long long)b * nq + head) * 128 + c8 * 8
-                                : kc + (((long long)b * nkv + (head - nq)) * ctx_max + p) * 128 + c8 * 8;
-        *reinterpret_cast<uint4*>(dst) = pack8(o1);
-        *reinterpret_cast<uint4*>(dst + 64) = pack8(o2);
+        if (head < nq) {
+            bf16* dst = q_out + ((long long)b * nq + head) * 128 + c8 * 8;
+            *reinterpret_cast<uint4*>(dst) = pack8(o1);
+            *reinterpret_cast<uint4*>(dst + 64) = pack8(o2);
+        } else {
+            bf16* stripe = kc + ((long long)b * nkv + (head - nq)) * ctx_max * 128;
+            *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, c8 * 8)) = pack8(o1);
+            *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, 64 + c8 * 8)) = pack8(o2);
+        }
     } else {
-        bf16* dst = vc + (((long long)b * nkv + (head - nq - nkv)) * ctx_max + p) * 128 + c8 * 8;
-        *reinterpret_cast<uint4*>(dst) = pack8(x1);
-        *reinterpret_cast<uint4*>(dst + 64) = pack8(x2);
+        bf16* stripe = vc + ((long long)b * nkv + (head - nq - nkv)) * ctx_max * 128;
+        *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, c8 * 8)) = pack8(x1);
+        *reinterpret_cast<uint4*>(stripe + kv_tiled_off(p, 64 + c8 * 8)) = pack8(x2);
     }
 }
 
@@ -705,10 +713,12 @@ extern "C" int dots_argmax_advance(const void* logits, long long ldl, int batch,
 }
 
 extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
-                                         void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, void* stream) {
+                                         void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, int tile_rows,
+                                         void* stream) {
     DOTS_REQUIRE(batch > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_embed_rmsnorm: H %% 8, H <= 2048");
     DOTS_REQUIRE(n_counters >= 0 && (n_counters == 0 || counters), "dots_decode_embed_rmsnorm: n_counters without a counter array");
-    DOTS_CHECK_CUDA(launch_ex(decode_embed_rmsnorm_kernel, dim3((batch + 7) / 8), dim3(256), (size_t)(0), ST(stream), true, ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid, (bf16*)normed, batch, H, eps, counters, n_counters));
+    DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && H % 64 == 0), "dots_decode_embed_rmsnorm: bad tile_rows %d", tile_rows);
+    DOTS_CHECK_CUDA(launch_ex(decode_embed_rmsnorm_kernel, dim3((batch + 7) / 8), dim3(256), (size_t)(0), ST(stream), true, ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid, (bf16*)normed, batch, H, eps, counters, n_counters, tile_rows));
     return 0;
 }
 

@@ -31,6 +31,10 @@ struct GemmParams {
     const bf16* bias;
     const bf16* res;
     long long ldr;
+    // decode (swap-AB) only: operands pre-tiled in HBM and fetched with 1-D bulk copies instead of tensor-map boxes
+    const uint8_t* a_tiled;        // ops.tile_weight(W): [m_blocks][num_k_blocks] blobs of 16 KB; nullptr: tmap_a
+    const uint8_t* b_tiled;        // activations, k-block-tiled with BLOCK_N rows per tile (ops.tile_rows); nullptr: tmap_b
+    int out_tiled;                 // SWIGLU_T: act is written k-block-tiled with BLOCK_N rows per tile (B operand of down_proj)
 };
 
 constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
@@ -147,7 +151,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int row,
                             const float other = __bfloat162float(xch[(keep0 + j) * 64 + fl]);
                             const float gv = is_up ? other : bf16_round(mine[j]);
                             const float uv = is_up ? bf16_round(mine[j]) : other;
-                            out[(long long)b * p.ldo + f] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
+                            const long long o = p.out_tiled ? tiled_row_off(b, f, BLOCK_N) : (long long)b * p.ldo + f;
+                            out[o] = __float2bfloat16_rn(bf16_round(silu_f(gv)) * uv);
                         }
                     }
                 }
@@ -288,8 +293,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&tmap_a);
-        prefetch_tensormap(&tmap_b);
+        if (!p.a_tiled) prefetch_tensormap(&tmap_a);
+        if (!p.b_tiled) prefetch_tensormap(&tmap_b);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -317,6 +322,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // operand fetch of one ring stage: a tensor-map box, or (decode, pre-tiled operands) one contiguous bulk copy
+            auto load_a = [&](int st, int kb, int m_blk) {
+                if (p.a_tiled) bulk_load(smem_a + st * S::A_BYTES, p.a_tiled + ((size_t)m_blk * p.num_k_blocks + kb) * S::A_BYTES, S::A_BYTES, &full_bar[st]);
+                else tma_load_2d(smem_a + st * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[st]);
+            };
+            auto load_b = [&](int st, int kb, int n_blk) {
+                if (p.b_tiled) bulk_load(smem_b + st * S::B_BYTES, p.b_tiled + (size_t)kb * S::B_BYTES, S::B_BYTES, &full_bar[st]);
+                else tma_load_2d(smem_b + st * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[st]);
+            };
             // Weights never depend on a predecessor kernel: put the first ring-full of weight tiles in flight BEFORE
             // waiting for the dependency, so HBM keeps streaming across the kernel boundary.
             int pre = 0;
@@ -328,7 +342,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
                     mbar_expect_tx(&full_bar[pre], S::STAGE_BYTES);
                     if (p.static_is_b) tma_load_2d(smem_b + pre * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[pre]);
-                    else tma_load_2d(smem_a + pre * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[pre]);
+                    else load_a(pre, kb, m_blk);
                 }
             }
             pdl_wait();
@@ -341,13 +355,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = kb0; kb < kb1; ++kb, ++issued) {
                     if (issued < pre) {
                         // static half already in flight on this stage's barrier: add the dependent half
-                        if (p.static_is_b) tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
-                        else tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[stage]);
+                        if (p.static_is_b) load_a(stage, kb, m_blk);
+                        else load_b(stage, kb, n_blk);
                     } else {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, &full_bar[stage]);
-                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, &full_bar[stage]);
+                        load_a(stage, kb, m_blk);
+                        load_b(stage, kb, n_blk);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -764,4 +778,56 @@ extern "C" int dots_gemm_skinny_swiglu_bf16(const void* X, long long ldx, const 
         case 128: return launch_gemm<128, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
         default: return launch_gemm<256, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
     }
+}
+
+// ---- decode GEMMs over pre-tiled operands (1-D bulk copies; see ops.tile_weight / ops.tile_rows) ----
+// gate|up projection + SwiGLU of one decode step, batch <= 64.  Wt = tile_weight(interleaved gate|up weight [2I, K]); Xt = normalised
+// activations, k-block-tiled with 32 / 64 rows per tile; act_t = bf16(bf16(silu(bf16 g)) * bf16 u), written k-block-tiled (same rows
+// per tile): the B operand of down_proj.
+extern "C" int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act_t, int batch, int two_i, int K, void* stream) {
+    DOTS_REQUIRE(Xt && Wt && act_t && batch > 0 && batch <= 64 && two_i > 0 && two_i % 128 == 0 && K > 0,
+                 "dots_decode_gemm_swiglu: bad arguments batch=%d 2I=%d K=%d", batch, two_i, K);
+    DOTS_REQUIRE((two_i / 2) % 64 == 0, "dots_decode_gemm_swiglu: I must be a multiple of 64 (tiled output)");
+    GemmParams p{};
+    p.static_is_b = 0;
+    p.M = two_i; p.N = batch; p.K = K;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb_per_split = p.num_k_blocks;
+    p.splits = 1;
+    p.out = act_t; p.ldo = two_i / 2;
+    p.m_blocks = two_i / BLOCK_M;
+    p.n_blocks = 1;
+    p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
+    p.b_tiled = reinterpret_cast<const uint8_t*>(Xt);
+    p.out_tiled = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta{}, tb{};            // unused with tiled operands
+    return batch <= 32 ? launch_gemm<32, DOTS_EPI_SWIGLU_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
+}
+
+// lm_head of one decode step, batch <= 64: out[b, n] = bf16(X[b, :] . W[n, :]).  Wt = tile_weight(W).  The activations are either
+// k-block-tiled (x_tile_rows = 32 / 64: Xt) or row-major (x_tile_rows = 0: X with pitch ldx, fetched through a tensor map).
+extern "C" int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_rows, const void* Wt, void* out_bf16, long long ldo, int batch,
+                                     int N, int K, void* stream) {
+    DOTS_REQUIRE(X && Wt && out_bf16 && batch > 0 && batch <= 64 && N > 0 && K > 0, "dots_decode_gemm_head: bad arguments batch=%d N=%d K=%d", batch, N, K);
+    const int bn = batch <= 32 ? 32 : 64;
+    DOTS_REQUIRE(x_tile_rows == 0 || x_tile_rows == bn, "dots_decode_gemm_head: x_tile_rows must be 0 or %d for batch %d", bn, batch);
+    GemmParams p{};
+    p.static_is_b = 0;
+    p.M = N; p.N = batch; p.K = K;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb_per_split = p.num_k_blocks;
+    p.splits = 1;
+    p.out = out_bf16; p.ldo = ldo;
+    p.m_blocks = (N + BLOCK_M - 1) / BLOCK_M;
+    p.n_blocks = 1;
+    p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta{}, tb{};
+    if (x_tile_rows) p.b_tiled = reinterpret_cast<const uint8_t*>(X);
+    else {
+        DOTS_REQUIRE(K % 8 == 0 && ldx % 8 == 0, "dots_decode_gemm_head: K and ldx must be multiples of 8");
+        if (make_tmap_2d_bf16(&tb, X, batch, K, ldx, bn)) return -4;
+    }
+    return bn == 32 ? launch_gemm<32, DOTS_EPI_BF16_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_BF16_T>(ta, tb, p, st);
 }

@@ -82,6 +82,27 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous, 16-byte aligned, size % 16 == 0), completion on an mbarrier (bytes).  One
+// request stream per copy: on B200 this streams > 100 GB/s per SM, where a 2-D tensor-map copy of 128-byte rows (one L2
+// request per row) stays near 40 GB/s per SM -- see tools/microbench.cu.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- pre-tiled HBM layouts (dots_ocr_b200/ops.py: tile_weight / tile_rows / kv_tile)
+// element offset of activation element (row b, column k) in the k-block-tiled layout with `rows` rows per tile:
+// [k / 64][rows x 64] blobs, 16-byte chunks XOR-swizzled by (b & 7) -- the SWIZZLE_128B image of a [rows x 64] K-major box
+__device__ __forceinline__ long long tiled_row_off(int b, int k, int rows) {
+    return (long long)(k >> 6) * (rows * 64) + b * 64 + ((((k & 63) >> 3) ^ (b & 7)) << 3) + (k & 7);
+}
+// element offset of (key j, dim d) inside one (sequence, kv head) stripe of the KV cache: per 64-key tile a 16 KB blob
+// [dims 0-63 | dims 64-127][64 keys][8 chunks swizzled by key & 7]
+__device__ __forceinline__ long long kv_tiled_off(long long j, int d) {
+    const int r = (int)(j & 63), c = d >> 3;
+    return (j >> 6) * 8192 + (c >> 3) * 4096 + r * 64 + (((c & 7) ^ (r & 7)) << 3) + (d & 7);
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)

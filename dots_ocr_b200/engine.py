@@ -152,13 +152,19 @@ class Engine:
                                W(p + "self_attn.v_proj.weight")], dim=0).contiguous()
             qkv_b = torch.cat([W(p + "self_attn.q_proj.bias"), W(p + "self_attn.k_proj.bias"),
                                W(p + "self_attn.v_proj.bias")], dim=0).contiguous()
-            self.t_layers.append(dict(
+            L = dict(
                 ln1=W(p + "input_layernorm.weight"), qkv_w=qkv_w, qkv_b=qkv_b, o=W(p + "self_attn.o_proj.weight"),
                 ln2=W(p + "post_attention_layernorm.weight"),
                 gu=_interleave_gate_up(W(p + "mlp.gate_proj.weight"), W(p + "mlp.up_proj.weight")),
-                down=W(p + "mlp.down_proj.weight")))
+                down=W(p + "mlp.down_proj.weight"))
+            # second copy for the decode step: 128 x 64 tiles stored as contiguous 16 KB blobs in the tensor cores' shared-memory
+            # image, so that a ring stage is one bulk copy (ops.tile_weight; +3.1 GB at full size)
+            for k in ("qkv_w", "o", "gu", "down"):
+                L[k + "_t"] = ops.tile_weight(L[k])
+            self.t_layers.append(L)
         self.final_norm = W("model.norm.weight")
         self.lm_head = W("lm_head.weight")
+        self.lm_head_t = ops.tile_weight(self.lm_head)
         hd = t.head_dim
         self.t_inv_freq = (1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -328,18 +334,21 @@ class Engine:
         scale = hd ** -0.5
         n_layers = len(self.t_layers)
         if pl["fused"]:
-            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps,
-                                     counters=st["counters"])
+            R = st["tile_rows"]
+            H, I = t.hidden_size, t.intermediate_size
+            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps,
+                                     counters=st["counters"], tile_rows=R)
             for li, L in enumerate(self.t_layers):
                 nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
-                ops.decode_gemm_qkv(st["normed"], L["qkv_w"], L["qkv_b"], st["qkv"])
-                ops.attn_decode_qkv(st["qkv"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li], st["ctx_len"], st["attn"], nq, nkv,
-                                    st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"])
-                ops.decode_gemm_resnorm(st["attn"], L["o"], st["resid"], L["ln2"], st["normed"], st["stats"][0], st["counters"][2 * li:2 * li + 1],
-                                        t.rms_norm_eps)
-                ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
-                ops.decode_gemm_resnorm(st["act"], L["down"], st["resid"], nxt, st["normed"], st["stats"][1],
-                                        st["counters"][2 * li + 1:2 * li + 2], t.rms_norm_eps)
+                ops.decode_gemm_qkv(st["normed_t"], L["qkv_w_t"], L["qkv_b"], st["qkv"], H)
+                ops.attn_decode_qkv(st["qkv"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li], st["ctx_len"], st["attn_t"], nq, nkv,
+                                    st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"], out_tile_rows=R)
+                ops.decode_gemm_resnorm(st["attn_t"], L["o_t"], st["resid"], L["ln2"], st["normed_t"], st["stats"][0],
+                                        st["counters"][2 * li:2 * li + 1], t.rms_norm_eps, nq * hd)
+                ops.decode_gemm_swiglu(st["normed_t"], L["gu_t"], st["act_t"], st["resid"].shape[0], H)
+                ops.decode_gemm_resnorm(st["act_t"], L["down_t"], st["resid"], nxt, st["normed_t"], st["stats"][1],
+                                        st["counters"][2 * li + 1:2 * li + 2], t.rms_norm_eps, I)
+            ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
         else:
             ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
             for li, L in enumerate(self.t_layers):
@@ -352,7 +361,7 @@ class Engine:
                 ops.gemm_skinny_swiglu(st["normed"], L["gu"], st["act"])
                 ops.gemm_skinny(st["act"], L["down"], pl["down"], partial=st["partial"])
                 ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed"], t.rms_norm_eps)
-        ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
+            ops.gemm_skinny(st["normed"], self.lm_head, 1, out_bf16=st["logits"])
         ops.argmax_advance(st["logits"], st["last"], st["out_ids"], st["step"], st["pos"], st["ctx_len"], st["finished"],
                            st["stops"], st["pad"], st["forced"])
 
@@ -382,6 +391,11 @@ class Engine:
         st["finished"] = torch.zeros(B, device=dev, dtype=torch.int32)
         st["forced"] = forced_ids.to(dev).long().contiguous() if forced_ids is not None else None
         st["qkv"] = torch.empty((B, (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim), device=dev, dtype=torch.bfloat16)
+        if pl["fused"]:
+            # k-block-tiled activation buffers of the bulk-copy decode path (rows beyond the batch stay zero)
+            R = st["tile_rows"] = ops.decode_tile_rows(B)
+            tiled = lambda k: torch.zeros(-(-k // 64) * R * 64, device=dev, dtype=torch.bfloat16)
+            st["normed_t"], st["attn_t"], st["act_t"] = tiled(H), tiled(t.num_attention_heads * t.head_dim), tiled(t.intermediate_size)
         st["stats"] = torch.zeros((2, -(-H // 128) * 64), device=dev, dtype=torch.float32)
         st["counters"] = torch.zeros(2 * t.num_hidden_layers, device=dev, dtype=torch.int32)
         return st
@@ -390,7 +404,7 @@ class Engine:
         """bf16 bytes every decode step must stream: all decoder-layer weights + final norm + lm_head."""
         n = self.final_norm.numel() + self.lm_head.numel()
         for L in self.t_layers:
-            n += sum(v.numel() for v in L.values())
+            n += sum(v.numel() for k, v in L.items() if not k.endswith("_t"))       # the tiled copies are the same parameters
         return 2 * n
 
     def decode_bytes(self, B: int, seq_lens, n_steps: int) -> float:

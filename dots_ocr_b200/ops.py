@@ -320,39 +320,82 @@ def argmax_advance(logits, next_ids, out_ids=None, step=None, pos=None, ctx_len=
     _lib.check(rc, "dots_argmax_advance")
 
 
-def decode_embed_rmsnorm(ids, table, w, resid, normed, eps, counters=None):
+def decode_embed_rmsnorm(ids, table, w, resid, normed, eps, counters=None, tile_rows: int = 0):
+    """tile_rows > 0: ``normed`` is written k-block-tiled (the B operand of the cluster GEMMs), else row-major."""
     V, H = table.shape
     if counters is not None:
         assert counters.dtype == torch.int32 and counters.is_cuda
     rc = _lib.load().dots_decode_embed_rmsnorm(_p(ids), _p(table), _ll(V), _p(w), _p(resid), _p(normed), ids.numel(), H,
-                                               C.c_float(eps), _p(counters), 0 if counters is None else counters.numel(), _stream())
+                                               C.c_float(eps), _p(counters), 0 if counters is None else counters.numel(), int(tile_rows), _stream())
     _lib.check(rc, "dots_decode_embed_rmsnorm")
 
 
-def decode_gemm_qkv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
-    """q|k|v projection of a decode step (batch <= 64), split-K reduced inside thread-block clusters: out = bf16(x @ w.T + bias)."""
-    _bf16_2d(x, "x"); _bf16_2d(w, "w"); _bf16_2d(out, "out")
-    B, Kd = x.shape
-    N = w.shape[0]
-    assert out.shape == (B, N)
-    rc = _lib.load().dots_decode_gemm_qkv(_p(x), _ll(x.stride(0)), _p(w), _ll(w.stride(0)), _p(bias), _p(out), _ll(out.stride(0)), B, N, Kd,
-                                          _stream())
+def decode_tile_rows(batch: int) -> int:
+    """Rows per tile of the k-block-tiled activation buffers of a decode step with this batch size."""
+    assert 0 < batch <= 64
+    return 32 if batch <= 32 else 64
+
+
+def _tiled_act_ok(t: torch.Tensor, batch: int, K: int, name: str) -> None:
+    need = -(-K // 64) * decode_tile_rows(batch) * 64
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() >= need):
+        raise ValueError(f"{name}: need a contiguous CUDA bf16 buffer of >= {need} elements (k-block-tiled [{batch}, {K}]), got {t.dtype} {tuple(t.shape)}")
+
+
+def _tiled_w_ok(wt: torch.Tensor, N: int, K: int, name: str) -> None:
+    if not (wt.is_cuda and wt.dtype == torch.bfloat16 and wt.is_contiguous() and tuple(wt.shape) == (-(-N // 128), -(-K // 64), 128 * 64)):
+        raise ValueError(f"{name}: need ops.tile_weight(W) of a [{N}, {K}] weight, got {tuple(wt.shape)}")
+
+
+def decode_gemm_qkv(xt: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, K: int) -> torch.Tensor:
+    """q|k|v projection of a decode step (batch <= 64), split-K reduced inside thread-block clusters: out = bf16(x @ w.T + bias).
+    xt: k-block-tiled activations [batch, K]; wt = tile_weight(w)."""
+    _bf16_2d(out, "out")
+    B, N = out.shape
+    _tiled_act_ok(xt, B, K, "xt"); _tiled_w_ok(wt, N, K, "wt")
+    rc = _lib.load().dots_decode_gemm_qkv(_p(xt), _p(wt), _p(bias), _p(out), _ll(out.stride(0)), B, N, K, _stream())
     _lib.check(rc, "dots_decode_gemm_qkv")
     return out
 
 
-def decode_gemm_resnorm(x: torch.Tensor, w: torch.Tensor, resid: torch.Tensor, ln_w: torch.Tensor, normed: torch.Tensor, stats: torch.Tensor,
-                        counter: torch.Tensor, eps: float) -> None:
+def decode_gemm_resnorm(xt: torch.Tensor, wt: torch.Tensor, resid: torch.Tensor, ln_w: torch.Tensor, normed_t: torch.Tensor, stats: torch.Tensor,
+                        counter: torch.Tensor, eps: float, K: int) -> None:
     """o_proj / down_proj of a decode step with residual add and the next RMSNorm fused (batch <= 64):
-    resid += bf16(x @ w.T); normed = RMSNorm(resid) * ln_w.  ``counter``: one zeroed int32 (re-armed by decode_embed_rmsnorm)."""
-    _bf16_2d(x, "x"); _bf16_2d(w, "w"); _bf16_2d(resid, "resid"); _bf16_2d(normed, "normed")
-    B, Kd = x.shape
-    N = w.shape[0]
-    assert resid.shape == (B, N) and normed.shape == (B, N) and resid.is_contiguous() and normed.is_contiguous()
+    resid += bf16(x @ w.T) (row-major); normed_t = RMSNorm(resid) * ln_w (k-block-tiled).  ``counter``: one zeroed int32."""
+    _bf16_2d(resid, "resid")
+    B, N = resid.shape
+    assert resid.is_contiguous()
+    _tiled_act_ok(xt, B, K, "xt"); _tiled_act_ok(normed_t, B, N, "normed_t"); _tiled_w_ok(wt, N, K, "wt")
     assert stats.dtype == torch.float32 and stats.numel() >= -(-N // 128) * 64 and counter.dtype == torch.int32
-    rc = _lib.load().dots_decode_gemm_resnorm(_p(x), _ll(x.stride(0)), _p(w), _ll(w.stride(0)), _p(resid), _p(ln_w), _p(normed), _p(stats),
-                                              _p(counter), B, N, Kd, C.c_float(eps), _stream())
+    rc = _lib.load().dots_decode_gemm_resnorm(_p(xt), _p(wt), _p(resid), _p(ln_w), _p(normed_t), _p(stats), _p(counter), B, N, K, C.c_float(eps),
+                                              _stream())
     _lib.check(rc, "dots_decode_gemm_resnorm")
+
+
+def decode_gemm_swiglu(xt: torch.Tensor, wt: torch.Tensor, act_t: torch.Tensor, batch: int, K: int) -> torch.Tensor:
+    """gate|up + SwiGLU of a decode step over tiled operands; act_t (k-block-tiled [batch, I]) is the B operand of down_proj."""
+    two_i = wt.shape[0] * 128
+    _tiled_act_ok(xt, batch, K, "xt"); _tiled_act_ok(act_t, batch, two_i // 2, "act_t"); _tiled_w_ok(wt, two_i, K, "wt")
+    rc = _lib.load().dots_decode_gemm_swiglu(_p(xt), _p(wt), _p(act_t), batch, two_i, K, _stream())
+    _lib.check(rc, "dots_decode_gemm_swiglu")
+    return act_t
+
+
+def decode_gemm_head(x: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, N: int, K: int, tiled: bool) -> torch.Tensor:
+    """lm_head of a decode step: out [batch, N] = bf16(x @ w.T); x k-block-tiled (tiled=True) or row-major [batch, K]."""
+    _bf16_2d(out, "out")
+    B = out.shape[0]
+    _tiled_w_ok(wt, N, K, "wt")
+    if tiled:
+        _tiled_act_ok(x, B, K, "x")
+        ldx, rows = 0, decode_tile_rows(B)
+    else:
+        _bf16_2d(x, "x")
+        assert x.shape == (B, K)
+        ldx, rows = x.stride(0), 0
+    rc = _lib.load().dots_decode_gemm_head(_p(x), _ll(ldx), rows, _p(wt), _p(out), _ll(out.stride(0)), B, N, K, _stream())
+    _lib.check(rc, "dots_decode_gemm_head")
+    return out
 
 
 def decode_gemm_max_clusters(batch: int) -> int:
@@ -362,13 +405,17 @@ def decode_gemm_max_clusters(batch: int) -> int:
 
 
 def attn_decode_qkv(qkv, pos, inv_freq, k_cache, v_cache, ctx_len, out, n_q_heads: int, n_kv_heads: int, ctx_max: int, n_splits: int,
-                    scale: float, part_o=None, part_ml=None, head_dim: int = 128):
-    """RoPE + KV append + decode attention from the bf16 q|k|v row of decode_gemm_qkv."""
-    B = out.shape[0]
+                    scale: float, part_o=None, part_ml=None, head_dim: int = 128, out_tile_rows: int = 0):
+    """RoPE + KV append + decode attention from the bf16 q|k|v row of decode_gemm_qkv.  out_tile_rows > 0: ``out`` is a k-block-tiled
+    activation buffer (B operand of o_proj), else row-major [B, n_q_heads * 128]."""
     _bf16_2d(qkv, "qkv")
+    B = qkv.shape[0]
     assert qkv.is_contiguous() and ctx_len.dtype == torch.int32 and pos.dtype == torch.int32
-    rc = _lib.load().dots_attn_decode_qkv(_p(qkv), _p(pos), _p(inv_freq), _p(k_cache), _p(v_cache), _p(ctx_len), _p(out), _p(part_o),
-                                          _p(part_ml), B, n_q_heads, n_kv_heads, head_dim, _ll(ctx_max), n_splits, C.c_float(scale), _stream())
+    if out_tile_rows:
+        _tiled_act_ok(out, B, n_q_heads * head_dim, "out")
+    rc = _lib.load().dots_attn_decode_qkv(_p(qkv), _p(pos), _p(inv_freq), _p(k_cache), _p(v_cache), _p(ctx_len), _p(out), int(out_tile_rows),
+                                          _p(part_o), _p(part_ml), B, n_q_heads, n_kv_heads, head_dim, _ll(ctx_max), n_splits, C.c_float(scale),
+                                          _stream())
     _lib.check(rc, "dots_attn_decode_qkv")
     return out
 
@@ -480,3 +527,68 @@ def capture(fn) -> Graph:
         with g:
             fn()
         return g
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pre-tiled HBM layouts of the decode step.  A 2-D tensor-map copy of a [rows x 128 B] box costs one L2 request per row
+# and tops out near 40 GB/s per SM on B200, a 1-D bulk copy of the same bytes streams at > 100 GB/s per SM
+# (profiles/microbench_r2.md).  Everything a decode step streams is therefore stored as contiguous blobs that already
+# have the shared-memory image the tensor cores / ldmatrix expect (128-byte rows, 16-byte chunks XOR-swizzled by row & 7,
+# i.e. what a SWIZZLE_128B tensor-map copy would have produced) and is fetched with cp.async.bulk.
+# ---------------------------------------------------------------------------------------------------------------------
+def _swizzle_chunks(t: torch.Tensor) -> torch.Tensor:
+    """t [..., rows, 8 chunks, 8 elems]: chunk p of row r receives source chunk p ^ (r & 7)."""
+    rows = t.shape[-3]
+    r7 = (torch.arange(rows, device=t.device) & 7).view(rows, 1)
+    src = (torch.arange(8, device=t.device).view(1, 8) ^ r7)                     # [rows, 8]
+    idx = src.view(*([1] * (t.dim() - 3)), rows, 8, 1).expand(*t.shape)
+    return t.gather(-2, idx)
+
+
+def tile_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] bf16 nn.Linear weight -> [ceil(N/128), ceil(K/64), 128 x 64] blobs of 16 KB (zero padded), each the K-major
+    SWIZZLE_128B image of that 128-row x 64-column tile: the A operand of a swap-AB decode GEMM stage in ONE bulk copy."""
+    assert w.dim() == 2 and w.dtype == torch.bfloat16
+    N, K = w.shape
+    Np, Kp = -(-N // 128) * 128, -(-K // 64) * 64
+    if (Np, Kp) != (N, K):
+        wp = torch.zeros((Np, Kp), device=w.device, dtype=w.dtype)
+        wp[:N, :K] = w
+        w = wp
+    t = w.view(Np // 128, 128, Kp // 64, 8, 8).permute(0, 2, 1, 3, 4)            # [tile, kb, r, c, e]
+    return _swizzle_chunks(t).contiguous().view(Np // 128, Kp // 64, 128 * 64)
+
+
+def tile_rows(x: torch.Tensor, rows_per_tile: int) -> torch.Tensor:
+    """[B <= rows_per_tile, K] bf16 activations -> [ceil(K/64), rows_per_tile x 64] blobs (the B operand of one k-block)."""
+    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.shape[0] <= rows_per_tile and rows_per_tile % 8 == 0
+    B, K = x.shape
+    Kp = -(-K // 64) * 64
+    xp = torch.zeros((rows_per_tile, Kp), device=x.device, dtype=x.dtype)
+    xp[:B, :K] = x
+    t = xp.view(rows_per_tile, Kp // 64, 8, 8).permute(1, 0, 2, 3)               # [kb, r, c, e]
+    return _swizzle_chunks(t).contiguous().view(Kp // 64, rows_per_tile * 64)
+
+
+def untile_rows(t: torch.Tensor, B: int, K: int) -> torch.Tensor:
+    """Inverse of tile_rows: [ceil(K/64), rows x 64] -> [B, K]."""
+    kb, n = t.shape
+    rows = n // 64
+    u = _swizzle_chunks(t.view(kb, rows, 8, 8))                                   # the XOR swizzle is its own inverse
+    return u.permute(1, 0, 2, 3).reshape(rows, kb * 64)[:B, :K].contiguous()
+
+
+def kv_tile(x: torch.Tensor) -> torch.Tensor:
+    """[..., ctx, 128] (ctx % 64 == 0) row-major keys or values -> the cache layout: per 64-key tile a 16 KB blob
+    [dims 0-63 | dims 64-127][64 keys][8 chunks swizzled by key & 7] (same shape, different element order)."""
+    assert x.shape[-1] == 128 and x.shape[-2] % 64 == 0
+    lead, ctx = x.shape[:-2], x.shape[-2]
+    t = x.reshape(*lead, ctx // 64, 64, 2, 8, 8).transpose(-4, -3)               # [..., tile, half, key, c, e]
+    return _swizzle_chunks(t).contiguous().view(*lead, ctx, 128)
+
+
+def kv_untile(x: torch.Tensor) -> torch.Tensor:
+    """Inverse of kv_tile (tests / debugging): cache layout -> [..., ctx, 128] row-major."""
+    lead, ctx = x.shape[:-2], x.shape[-2]
+    t = _swizzle_chunks(x.reshape(*lead, ctx // 64, 2, 64, 8, 8))
+    return t.transpose(-4, -3).reshape(*lead, ctx, 128).contiguous()

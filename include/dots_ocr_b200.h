@@ -92,7 +92,12 @@ DOTS_API int dots_attn_varlen_fwd_tc(const void* q, long long q_stride, const vo
                             int max_seqlen, long long total_tokens, int n_q_heads, int n_kv_heads, int head_dim,
                             int causal, float softmax_scale, void* stream);
 
-/* One-token-per-sequence attention over the KV cache [batch, n_kv_heads, ctx_max, 128]
+/* KV CACHE LAYOUT (all entry points that touch k_cache / v_cache): [batch, n_kv_heads, ctx_max, 128] bf16 with ctx_max % 64 == 0;
+ * inside each (sequence, kv head) stripe the keys are stored in 64-key tiles of 16 KB whose byte order is the shared-memory image
+ * the decode attention kernel consumes -- [dims 0-63 | dims 64-127][64 keys][128-byte row, 16-byte chunks XOR-swizzled by key & 7]
+ * (ops.kv_tile / ops.kv_untile convert) -- so that one tile is ONE contiguous bulk copy instead of 128 row requests.
+ *
+ * One-token-per-sequence attention over the KV cache [batch, n_kv_heads, ctx_max, 128]
  * (replaces DynamicCache + sdpa/flash decode, transformers/cache_utils.py:102-120, [Q]:227-241).
  * ctx_len[b] = number of visible keys (current token's key already appended).
  * part_o [batch, n_q_heads, n_splits, 128] fp32 and part_ml [batch, n_q_heads, n_splits, 2] fp32 are
@@ -111,10 +116,12 @@ DOTS_API int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, co
                            long long ctx_max, int n_splits, float softmax_scale, void* stream);
 
 /* dots_attn_decode_fused with the current token's q|k|v as the bf16 row [batch][(n_q_heads + 2 n_kv_heads) * 128] written by
- * dots_decode_gemm_qkv (bias already added): RoPE at pos[b] + KV append + attention. */
+ * dots_decode_gemm_qkv (bias already added): RoPE at pos[b] + KV append + attention.  out_tile_rows > 0: `out` is written in the
+ * k-block-tiled activation layout (the B operand of dots_decode_gemm_resnorm) with that many rows per tile; 0: row-major. */
 DOTS_API int dots_attn_decode_qkv(const void* qkv_bf16, const int* pos, const float* inv_freq, void* k_cache, void* v_cache,
-                         const int* ctx_len, void* out, float* part_o, float* part_ml, int batch, int n_q_heads,
-                         int n_kv_heads, int head_dim, long long ctx_max, int n_splits, float softmax_scale, void* stream);
+                         const int* ctx_len, void* out, int out_tile_rows, float* part_o, float* part_ml, int batch,
+                         int n_q_heads, int n_kv_heads, int head_dim, long long ctx_max, int n_splits, float softmax_scale,
+                         void* stream);
 
 /* 1 (default): 2..4 key splits of a (sequence, kv head) run as one thread-block cluster and are merged through distributed
  * shared memory by the leader CTA (no partial buffers, no combine launch); 0: always the combine kernel. */
@@ -183,9 +190,11 @@ DOTS_API int dots_argmax_advance(const void* logits, long long ldl, int batch, i
 
 /* ---- decode-step fused finalize kernels (split-K reduce + HF rounding points) ------------------ */
 /* First kernel of a decode step: resid = embed[ids]; normed = RMSNorm(resid) * w; also zeroes counters[0..n_counters) -- the
- * rendezvous counters of this step's dots_decode_gemm_resnorm launches (counters may be NULL with n_counters == 0). */
+ * rendezvous counters of this step's dots_decode_gemm_resnorm launches (counters may be NULL with n_counters == 0).
+ * tile_rows = 32 / 64: normed is written k-block-tiled with that many rows per tile; 0: row-major [batch, H]. */
 DOTS_API int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
-                              void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, void* stream);
+                              void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, int tile_rows,
+                              void* stream);
 DOTS_API int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed,
                                  int batch, int H, float eps, void* stream);
 DOTS_API int dots_decode_qkv_rope_append(const float* partial, int splits, const void* bias, const int* pos,
@@ -193,23 +202,36 @@ DOTS_API int dots_decode_qkv_rope_append(const float* partial, int splits, const
                                 int batch, int n_q_heads, int n_kv_heads, int head_dim, void* stream);
 DOTS_API int dots_decode_swiglu(const float* partial, int splits, void* act, int batch, int inter, void* stream);
 
-/* ---- decode-step projections with the split-K reduction on chip (thread-block clusters + distributed shared memory) ---- */
+/* ---- decode-step projections over PRE-TILED operands, split-K reduction on chip ----------------------------------------
+ * Operand layouts (host helpers: ops.tile_weight / ops.tile_rows / ops.untile_rows; device: tiled_row_off in csrc/ptx.cuh):
+ *   Wt  weights [N, K] as [ceil(N/128)][ceil(K/64)] contiguous 16 KB blobs, each the K-major SWIZZLE_128B shared-memory image of a
+ *       128-row x 64-column tile (zero padded);
+ *   Xt  activations [batch, K] as [ceil(K/64)] blobs of R x 128 B (R = 32 for batch <= 32, else 64), same swizzle.
+ * One ring stage of these GEMMs is ONE 1-D bulk copy per operand: a tensor-map copy of 128-byte rows tops out near 40 GB/s per SM
+ * on B200 (one L2 request per row), a bulk copy streams > 100 GB/s per SM (profiles/microbench_r2.md). */
 
 /* q|k|v projection of one decode step, batch <= 64: out[b, n] = bf16(X[b, :] . W[n, :] + bias[n])  ([Q]:217-219, fused
- * q|k|v weight).  K is split over the 8 CTAs of a cluster per 128-row weight tile and reduced through distributed shared
- * memory in split order (deterministic); replaces dots_gemm_skinny_bf16(partials) + the reduction in its consumer. */
-DOTS_API int dots_decode_gemm_qkv(const void* X, long long ldx, const void* W, long long ldw, const void* bias, void* out,
-                         long long ldo, int batch, int N, int K, void* stream);
+ * q|k|v weight), out row-major with pitch ldo.  K is split over the 8 CTAs of a cluster per 128-row weight tile and reduced
+ * through distributed shared memory in split order (deterministic). */
+DOTS_API int dots_decode_gemm_qkv(const void* Xt, const void* Wt, const void* bias, void* out, long long ldo, int batch, int N,
+                         int K, void* stream);
 
 /* o_proj / down_proj of one decode step with everything up to the next GEMM's input fused, batch <= 64:
- *   x = bf16(bf16(X . W^T) + resid);  resid = x;  normed = bf16(bf16(x * rsqrt(mean x^2 + eps)) * ln_w)
- * ([Q]:243,302-308 and :46-48,308 + :258-263).  stats: scratch [ceil(N/128)][64] fp32; counter: one uint32 that is ZERO
- * when the kernel starts (the kernel's CTAs rendezvous on it once; dots_decode_embed_rmsnorm re-zeroes a block of counters at
- * the start of every step).  All ceil(N/128) clusters must be co-resident (checked: see dots_decode_gemm_max_clusters).
- * Replaces dots_gemm_skinny_bf16(partials) + dots_decode_residual_rmsnorm. */
-DOTS_API int dots_decode_gemm_resnorm(const void* X, long long ldx, const void* W, long long ldw, void* resid, const void* ln_w,
-                             void* normed, float* stats, unsigned int* counter, int batch, int N, int K, float eps,
-                             void* stream);
+ *   x = bf16(bf16(X . W^T) + resid);  resid = x (row-major [batch, N]);  normed_t = bf16(bf16(x * rsqrt(mean x^2 + eps)) * ln_w),
+ * written k-block-tiled ([Q]:243,302-308 and :46-48,308 + :258-263).  stats: scratch [ceil(N/128)][64] fp32; counter: one uint32
+ * that is ZERO when the kernel starts (the kernel's CTAs rendezvous on it once; dots_decode_embed_rmsnorm re-zeroes a block of
+ * counters at the start of every step).  All ceil(N/128) clusters must be co-resident (checked: dots_decode_gemm_max_clusters). */
+DOTS_API int dots_decode_gemm_resnorm(const void* Xt, const void* Wt, void* resid, const void* ln_w, void* normed_t, float* stats,
+                             unsigned int* counter, int batch, int N, int K, float eps, void* stream);
+
+/* gate|up projection + SwiGLU of one decode step, batch <= 64 (no split-K: 2I/128 tiles cover the SMs).  Wt = tiled interleaved
+ * gate|up weight [2I, K] (as DOTS_EPI_SWIGLU); act_t [batch, I] = bf16(bf16(silu(bf16 g)) * bf16 u), written k-block-tiled. */
+DOTS_API int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act_t, int batch, int two_i, int K, void* stream);
+
+/* lm_head of one decode step, batch <= 64: out[b, n] = bf16(X . W^T), row-major.  x_tile_rows = 32 / 64: X is k-block-tiled;
+ * x_tile_rows = 0: X is row-major with pitch ldx (first token after prefill). */
+DOTS_API int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_rows, const void* Wt, void* out_bf16, long long ldo,
+                          int batch, int N, int K, void* stream);
 
 /* Number of 8-CTA clusters of dots_decode_gemm_resnorm the current device keeps resident at once. */
 DOTS_API int dots_decode_gemm_max_clusters(int batch, int* out);

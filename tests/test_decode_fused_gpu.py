@@ -54,7 +54,8 @@ def test_decode_gemm_qkv(B, N, K, gen):
     ops = _ops()
     x, w, bias = _rand((B, K), gen), _rand((N, K), gen, 0.03), _rand((N,), gen)
     out = torch.full((B, N), float("nan"), device=DEV, dtype=torch.bfloat16)
-    ops.decode_gemm_qkv(x, w, bias, out)
+    R = ops.decode_tile_rows(B)
+    ops.decode_gemm_qkv(ops.tile_rows(x, R).view(-1), ops.tile_weight(w), bias, out, K)
     ref = _bf(x.float() @ w.float().t() + bias.float())
     assert not torch.isnan(out.float()).any()
     err = float((out.float() - ref.float()).abs().max() / ref.float().abs().max())
@@ -84,9 +85,11 @@ def test_decode_gemm_resnorm(B, N, K, gen):
     for rep in range(2):                                      # second round: counter re-armed, same answer
         counter = torch.zeros(1, device=DEV, dtype=torch.int32)
         resid = resid0.clone()
-        normed = torch.full((B, N), float("nan"), device=DEV, dtype=torch.bfloat16)
-        ops.decode_gemm_resnorm(x, w, resid, ln_w, normed, stats, counter, eps)
+        R = ops.decode_tile_rows(B)
+        normed_t = torch.full((N // 64 * R * 64,), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.decode_gemm_resnorm(ops.tile_rows(x, R).view(-1), ops.tile_weight(w), resid, ln_w, normed_t, stats, counter, eps, K)
         torch.cuda.synchronize()
+        normed = ops.untile_rows(normed_t.view(N // 64, R * 64), B, N)
         assert int(counter.item()) == tiles * 8
         # PyTorch restatement with HF's rounding points ([Q]:243,302-308, 258-263)
         y = _bf(x.float() @ w.float().t())
@@ -112,11 +115,11 @@ def test_decode_gemm_resnorm(B, N, K, gen):
 @pytest.mark.parametrize("B,nq,nkv,ctx,splits", [(64, 12, 2, 1881, 2), (8, 12, 2, 700, 4), (3, 6, 1, 130, 2), (5, 12, 2, 64, 3), (2, 12, 2, 5000, 4),
                                                   (4, 12, 2, 3000, 8), (64, 12, 2, 1881, 1)])
 def test_attention_from_bf16_qkv_and_cluster_merge(B, nq, nkv, ctx, splits, gen):
-    """dots_attn_decode_qkv (bf16 q|k|v row, cluster merge) == dots_attn_decode_fused (fp32 partials, combine kernel)."""
+    """dots_attn_decode_qkv (bf16 q|k|v row, cluster merge, row-major or tiled output) == dots_attn_decode_fused (fp32 partials, combine kernel)."""
     ops = _ops()
     N = (nq + 2 * nkv) * 128
     ctx_max = (ctx + 64 + 63) // 64 * 64
-    kc = _rand((B, nkv, ctx_max, 128), gen)
+    kc = _rand((B, nkv, ctx_max, 128), gen)                # random bits are as good in the tiled cache layout as in any other
     vc = _rand((B, nkv, ctx_max, 128), gen)
     lens = torch.randint(max(1, ctx - 90), ctx + 1, (B,), generator=gen, device=DEV)
     lens[0] = ctx
@@ -128,7 +131,8 @@ def test_attention_from_bf16_qkv_and_cluster_merge(B, nq, nkv, ctx, splits, gen)
     qkv = _bf((part[0] + part[1]) + part[2] + bias.float())
     scale = 128 ** -0.5
     outs = []
-    for mode in ("old_combine", "old_cluster", "new_cluster", "new_combine"):
+    R = ops.decode_tile_rows(B)
+    for mode in ("old_combine", "old_cluster", "new_cluster", "new_combine", "new_tiled_out"):
         k1, v1 = kc.clone(), vc.clone()
         out = torch.full((B, nq * 128), float("nan"), device=DEV, dtype=torch.bfloat16)
         ops.set_decode_cluster(mode.endswith("cluster"))
@@ -137,6 +141,10 @@ def test_attention_from_bf16_qkv_and_cluster_merge(B, nq, nkv, ctx, splits, gen)
             pml = torch.empty((B, nq, splits, 2), device=DEV, dtype=torch.float32)
             if mode.startswith("old"):
                 ops.attn_decode_fused(part, 3, bias, pos, inv_freq, k1, v1, ctx_len, out, nq, nkv, ctx_max, splits, scale, po, pml)
+            elif mode == "new_tiled_out":
+                out_t = torch.full((nq * 2 * R * 64,), float("nan"), device=DEV, dtype=torch.bfloat16)
+                ops.attn_decode_qkv(qkv, pos, inv_freq, k1, v1, ctx_len, out_t, nq, nkv, ctx_max, splits, scale, po, pml, out_tile_rows=R)
+                out = ops.untile_rows(out_t.view(nq * 2, R * 64), B, nq * 128)
             else:
                 ops.attn_decode_qkv(qkv, pos, inv_freq, k1, v1, ctx_len, out, nq, nkv, ctx_max, splits, scale, po, pml)
         finally:
@@ -151,8 +159,8 @@ def test_attention_from_bf16_qkv_and_cluster_merge(B, nq, nkv, ctx, splits, gen)
     for b in range(min(B, 4)):
         L = int(lens[b])
         q = _hf_rope_bf16(qkv[b:b + 1, : nq * 128].reshape(1, nq, 128), pos[b:b + 1], inv_freq)[0].float()      # [nq, 128]
-        kk = k1[b, :, :L].float().repeat_interleave(nq // nkv, 0)
-        vv = v1[b, :, :L].float().repeat_interleave(nq // nkv, 0)
+        kk = ops.kv_untile(k1[b])[:, :L].float().repeat_interleave(nq // nkv, 0)
+        vv = ops.kv_untile(v1[b])[:, :L].float().repeat_interleave(nq // nkv, 0)
         p = torch.softmax(torch.einsum("hd,hld->hl", q, kk) * scale, -1)
         ref = torch.einsum("hl,hld->hd", p, vv).reshape(-1)
         assert float((out[b].float() - ref).abs().max()) < 2e-2
@@ -223,3 +231,31 @@ def test_engine_fused_decode_matches_per_op_decode():
                           return_logits=True).logits.float().cpu()
         sd = float(res[False][1].std())
         assert float((lf - res[False][1]).abs().max()) / sd < 6e-2
+
+
+@pytest.mark.parametrize("B,I,K", [(64, 8960, 1536), (33, 4224, 1536), (1, 8960, 1536), (7, 1024, 768), (32, 1024, 768)])
+def test_decode_gemm_swiglu_tiled_operands(B, I, K, gen):
+    """Bulk-copied pre-tiled operands feed the same MMAs in the same order as the tensor-map kernel: bit-identical activations."""
+    from dots_ocr_b200.engine import _interleave_gate_up
+    ops = _ops()
+    x = _rand((B, K), gen)
+    w = _interleave_gate_up(_rand((I, K), gen, 0.03), _rand((I, K), gen, 0.03))
+    ref = ops.gemm_skinny_swiglu(x, w)
+    R = ops.decode_tile_rows(B)
+    act_t = torch.full((I // 64 * R * 64,), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.decode_gemm_swiglu(ops.tile_rows(x, R).view(-1), ops.tile_weight(w), act_t, B, K)
+    assert torch.equal(ops.untile_rows(act_t.view(I // 64, R * 64), B, I), ref)
+
+
+@pytest.mark.parametrize("B,N,K", [(64, 151936, 1536), (5, 2048, 768), (33, 4096, 1536)])
+def test_decode_gemm_head_tiled_operands(B, N, K, gen):
+    ops = _ops()
+    x, w = _rand((B, K), gen), _rand((N, K), gen, 0.03)
+    ref = torch.empty((B, N), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_skinny(x, w, 1, out_bf16=ref)
+    wt = ops.tile_weight(w)
+    R = ops.decode_tile_rows(B)
+    for tiled in (True, False):
+        out = torch.full((B, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.decode_gemm_head(ops.tile_rows(x, R).view(-1) if tiled else x, wt, out, N, K, tiled=tiled)
+        assert torch.equal(out, ref), tiled

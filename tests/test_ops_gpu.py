@@ -117,7 +117,7 @@ def test_attn_decode_fused_matches_unfused(gen):
     for (B, splits_qkv, n_splits, ctxs) in [(3, 8, 1, [5, 130, 64]), (2, 3, 4, [700, 2137]), (64, 8, 1, None), (1, 1, 16, [1])]:
         if ctxs is None:
             ctxs = [int(v) for v in torch.randint(1, 1900, (B,), generator=torch.Generator().manual_seed(5))]
-        ctx_max = max(ctxs) + 9
+        ctx_max = (max(ctxs) + 9 + 63) // 64 * 64
         part = torch.randn((splits_qkv, B, N), generator=gen, device=DEV)
         bias = _rand((N,), gen, 0.1)
         ctx = torch.tensor(ctxs, dtype=torch.int32, device=DEV)
@@ -246,6 +246,7 @@ def test_llm_rope_kv_append(gen):
     ref_k = _hf_rope_bf16(qkv[:, nq * 128:(nq + nkv) * 128].reshape(T, nkv, 128), pos, inv_freq)
     ref_v = qkv[:, (nq + nkv) * 128:].reshape(T, nkv, 128).clone()
     ops.llm_rope_kv_append(qkv, nq, nkv, pos, seq, inv_freq, kc, vc, ctx_max)
+    kc, vc = ops.kv_untile(kc), ops.kv_untile(vc)          # the cache is stored in 64-key tiles (include/dots_ocr_b200.h)
     assert _frac_exact(qkv[:, : nq * 128], ref_q) > 0.999 and _rel_err(qkv[:, : nq * 128], ref_q) < 8e-3
     for t in range(T):
         b, p = int(seq[t]), int(pos[t])
@@ -291,12 +292,12 @@ def test_attn_decode(B, hq, hkv, ctxs, splits, gen):
     ops = _ops()
     if ctxs is None:
         ctxs = [int(x) for x in torch.randint(1, 2000, (B,), generator=torch.Generator().manual_seed(3))]
-    ctx_max = max(ctxs) + 7
+    ctx_max = (max(ctxs) + 7 + 63) // 64 * 64
     q = _rand((B, hq * 128), gen)
     kc, vc = _rand((B, hkv, ctx_max, 128), gen), _rand((B, hkv, ctx_max, 128), gen)
     ctx = torch.tensor(ctxs, dtype=torch.int32, device=DEV)
     out = torch.empty_like(q)
-    ops.attn_decode(q, kc, vc, ctx, out, hq, hkv, ctx_max, splits, 128 ** -0.5)
+    ops.attn_decode(q, ops.kv_tile(kc), ops.kv_tile(vc), ctx, out, hq, hkv, ctx_max, splits, 128 ** -0.5)
     group = hq // hkv
     for b in range(B):
         L = ctxs[b]
@@ -390,7 +391,7 @@ def test_decode_finalize_kernels(gen):
     ref_n = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(torch.bfloat16) * w
     assert _frac_exact(normed, ref_n) > 0.999
     # qkv finalize + rope + append
-    nq, nkv, ctx_max = 12, 2, 40
+    nq, nkv, ctx_max = 12, 2, 64
     N = (nq + 2 * nkv) * 128
     part = torch.randn((3, B, N), generator=gen, device=DEV)
     bias = _rand((N,), gen, 0.1)
@@ -400,6 +401,7 @@ def test_decode_finalize_kernels(gen):
     kc = torch.zeros((B, nkv, ctx_max, 128), device=DEV, dtype=torch.bfloat16)
     vc = torch.zeros_like(kc)
     ops.decode_qkv_rope_append(part, 3, bias, pos, inv_freq, q_out, kc, vc, ctx_max, nq, nkv)
+    kc, vc = ops.kv_untile(kc), ops.kv_untile(vc)
     qkv = _bf((part[0] + part[1]) + part[2] + bias.float())
     ref_q = _hf_rope_bf16(qkv[:, : nq * 128].reshape(B, nq, 128), pos, inv_freq).reshape(B, -1)
     ref_k = _hf_rope_bf16(qkv[:, nq * 128:(nq + nkv) * 128].reshape(B, nkv, 128), pos, inv_freq)

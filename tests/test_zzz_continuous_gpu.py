@@ -1,15 +1,12 @@
 """Continuous batching on the device: the slot backend over the real engine (dots_ocr_b200/continuous.py:EngineSlots) must
 give every page exactly the ids a one-page ``generate`` gives it, whatever shares the cache with it and whenever it was
 admitted.  Tiny config, `random` checkpoint (the continuation depends on the whole context, so a row reading a neighbour's
-or a previous tenant's keys would show).
-
-NOT YET RUN ON HARDWARE when committed (round 1's GPU budget was spent): marked xfail(strict=False) so that the first run
-reports XPASS / xfail without turning the suite red; the mark goes away once it has passed on a B200."""
+or a previous tenant's keys would show).  (Passed on B200 in the round-1 driver run and in round 2's first GPU pass.)"""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="EngineSlots has not run on hardware yet")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

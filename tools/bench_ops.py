@@ -96,7 +96,7 @@ def main():
     if "decode" in only:
         for (B, ctx, splits) in [(64, 1881, 3), (64, 1881, 1), (64, 1881, 6), (1, 1881, 16), (32, 6200, 6)]:
             hq, hkv = 12, 2
-            ctx_max = ctx + 64
+            ctx_max = (ctx + 64 + 63) // 64 * 64
             q = rnd(B, hq * 128)
             kc, vc = rnd(B, hkv, ctx_max, 128), rnd(B, hkv, ctx_max, 128)
             cl = torch.full((B,), ctx, device=DEV, dtype=torch.int32)
