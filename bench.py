@@ -269,8 +269,10 @@ def run_gpu(args):
     cfg = config.PRESETS[args.preset]()
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev)
     eng = Engine(cfg, ck, dev)
-    if args.decode_fused is not None:
-        eng.decode_fused = bool(args.decode_fused)
+    if args.decode_mode:
+        eng.decode_mode = args.decode_mode
+    if args.attn_splits:
+        eng.attn_splits = args.attn_splits
     ck_cpu = {k: v.to("cpu") for k, v in ck.items()} if (world == 1 and not args.no_cpu_baseline and args.preset == "full") else None
     del ck
     torch.cuda.empty_cache()
@@ -356,8 +358,9 @@ def run_gpu(args):
         ach = by / (ms / 1e3) / 1e9
         tr = _decode_traffic()
         roof = {"kernel": ("decode step = one CUDA-graph launch: " + ("cluster split-K tcgen05 GEMMs (reduction, residual, RMSNorm on chip) + "
-                           "cluster-merged KV attention + gate|up SwiGLU GEMM + lm_head + argmax" if eng._decode_plan(B)["fused"] else
-                           "skinny tcgen05 GEMMs + KV attention + finalize kernels")),
+                           "cluster-merged KV attention + gate|up SwiGLU GEMM + lm_head + argmax" if eng._decode_plan(B)["mode"] == "fused" else
+                           "skinny swap-AB tcgen05 GEMMs (split-K) + KV attention + finalize kernels" +
+                           (", operands pre-tiled in HBM and bulk-copied" if eng._decode_plan(B)["mode"] == "tiled" else ""))),
                 "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
                 "peak_source": peaks["source"] + " (copy bandwidth)",
                 "launch": "one decode step (graph replay)", "algorithmic_bytes_per_launch": round(by / max(1, steps_dec)),
@@ -436,8 +439,9 @@ def main():
     ap.add_argument("--gemm-pair", dest="gemm_pair", type=int, default=None, choices=[0, 1],
                     help="CTA-pair (cta_group::2) kernel for the large prefill GEMMs (default: the library default)")
     ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
-    ap.add_argument("--decode-fused", dest="decode_fused", type=int, default=None, choices=[0, 1],
-                    help="1: 5-kernel decode layer (cluster GEMMs), 0: 7-kernel per-op layer (default: the engine default)")
+    ap.add_argument("--decode-mode", dest="decode_mode", default=None, choices=["tiled", "fused", "perop"],
+                    help="decode layer variant (default: the engine default); see Engine.decode_mode")
+    ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="force the key-split count of the decode attention")
     ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "mma"])
     args = ap.parse_args()
     global PAGE_HW

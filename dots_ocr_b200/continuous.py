@@ -65,9 +65,9 @@ class EngineSlots:
     # -- admission ------------------------------------------------------------------------------------------------------
     def prepare(self, image, prompt: str):
         """Host half of admission (runs in the scheduler thread before the GPU is touched): uint8 page + prompt ids."""
-        from .processing import preprocess_image_u8
-        page = preprocess_image_u8(image, self.min_pixels, self.max_pixels)
-        n_img = (page.shape[0] // 14) * (page.shape[1] // 14) // 4
+        from .processing import page_to_u8, model_image_tokens
+        page = page_to_u8(image)                               # original size: the resize runs on the GPU at admission
+        n_img = model_image_tokens(int(page.shape[0]), int(page.shape[1]), self.min_pixels, self.max_pixels)
         ids = self.tokenizer.encode_chat(prompt, n_img)
         if len(ids) > self.max_prompt:
             raise ValueError(f"prompt of {len(ids)} tokens exceeds the session's max_prompt {self.max_prompt}")
@@ -89,7 +89,7 @@ class EngineSlots:
             lens = torch.tensor(seq_lens, dtype=torch.int64, device=dev)
             cu = torch.zeros(len(rows) + 1, dtype=torch.int32, device=dev)
             cu[1:] = lens.cumsum(0).to(torch.int32)
-            image_embeds = eng.encode_pages_u8(pages)
+            image_embeds = eng.encode_pages_u8(pages, min_pixels=self.min_pixels, max_pixels=self.max_pixels)
             img_slots, count = ops.image_slots(ids_packed, eng.cfg.image_token_id)
             if int(count.item()) != image_embeds.shape[0]:
                 raise ValueError(f"image tokens in the prompts ({int(count.item())}) != image embedding rows ({image_embeds.shape[0]})")

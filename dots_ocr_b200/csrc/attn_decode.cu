@@ -517,11 +517,12 @@ extern "C" int dots_attn_decode(const void* q, const void* k_cache, const void* 
 }
 
 extern "C" int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, const void* qkv_bias, const int* pos, const float* inv_freq,
-                                      void* k_cache, void* v_cache, const int* ctx_len, void* out, float* part_o, float* part_ml,
+                                      void* k_cache, void* v_cache, const int* ctx_len, void* out, int out_tile_rows, float* part_o, float* part_ml,
                                       int batch, int n_q_heads, int n_kv_heads, int head_dim, long long ctx_max, int n_splits,
                                       float softmax_scale, void* stream) {
     DOTS_REQUIRE(qkv_partial && qkv_splits >= 1 && qkv_bias && pos && inv_freq, "dots_attn_decode_fused: missing QKV inputs");
     DecParams p{};
+    p.out_tile_rows = out_tile_rows;
     p.q = nullptr; p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.ctx_len = ctx_len;
     p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
     p.qkv_partial = qkv_partial; p.qkv_splits = qkv_splits; p.qkv_bias = (const bf16*)qkv_bias; p.pos = pos; p.inv_freq = inv_freq;

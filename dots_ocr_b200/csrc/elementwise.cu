@@ -285,6 +285,33 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int
     }
 }
 
+// ------------------------------------------------------------------ page resize (uint8 bicubic + antialias, integer arithmetic)
+// One separable pass of the resize the stock image processor runs on the CPU (Pillow's ImagingResample as ported to ATen for
+// uint8 tensors; torchvision resize(BICUBIC, antialias=True), image_processing_qwen2_vl.py:148-232):
+//     out[.., i, ..] = clip((2^(p-1) + sum_j in[.., xmin[i] + j, ..] * w[i][j]) >> p, 0, 255)        (int32, int16 taps)
+// The tap tables come from the host (dots_ocr_b200/resize.py), so the result equals the CPU resize bit for bit.
+// inner = bytes of one step along the resampled axis's inner neighbours (3 for the horizontal pass over HWC pixels, W * 3 for the
+// vertical pass); a thread produces one output byte, consecutive threads consecutive bytes.
+__global__ void resample_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long n_outer, int in_size, int out_size,
+                                   long long inner, const int* __restrict__ xmin, const int* __restrict__ xsize,
+                                   const short* __restrict__ w, int ksize, int prec) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const long long total = n_outer * out_size * inner;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long in_ = idx % inner;
+        const int i = (int)((idx / inner) % out_size);
+        const long long o = idx / (inner * out_size);
+        const uint8_t* src = in + (o * in_size + xmin[i]) * inner + in_;
+        const short* wi = w + (long long)i * ksize;
+        int acc = 1 << (prec - 1);
+        const int n = xsize[i];
+        for (int j = 0; j < n; ++j) acc += (int)src[(long long)j * inner] * (int)wi[j];
+        acc >>= prec;
+        out[idx] = (uint8_t)min(max(acc, 0), 255);
+    }
+}
+
 // ------------------------------------------------------------------ embedding + image scatter
 // slots[t] = rank of token t among image-pad tokens (masked_scatter order), or -1 for text tokens.
 __global__ void __launch_bounds__(1024) image_slots_kernel(const long long* __restrict__ ids, int T, long long image_token,
@@ -504,7 +531,7 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
 // [splits] strided reads of 32 B per thread, all independent, so the whole reduction is one round of loads.
 __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const float* __restrict__ partial, int splits,
                                                                       bf16* __restrict__ resid, const bf16* __restrict__ w,
-                                                                      bf16* __restrict__ normed, int B, int H, float eps) {
+                                                                      bf16* __restrict__ normed, int B, int H, float eps, int tile_rows) {
     pdl_wait();
     pdl_launch_dependents();
     __shared__ float s_part[8];
@@ -538,7 +565,8 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
         unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = bf16_round(x[j] * r) * g[j];
-        reinterpret_cast<uint4*>(normed + (long long)b * H)[c] = pack8(f);
+        bf16* dst = tile_rows > 0 ? normed + tiled_row_off(b, c * 8, tile_rows) : normed + (long long)b * H + c * 8;
+        *reinterpret_cast<uint4*>(dst) = pack8(f);
     }
 }
 
@@ -636,6 +664,31 @@ extern "C" int dots_patchify_u8(const void* img_hwc, int H, int W, int patch, in
     return 0;
 }
 
+extern "C" int dots_resize_bicubic_u8(const void* img_hwc, int H, int W, void* tmp, void* out, int rh, int rw, const int* xmin_x, const int* xsize_x,
+                                      const short* w_x, int ksize_x, int prec_x, const int* xmin_y, const int* xsize_y, const short* w_y, int ksize_y,
+                                      int prec_y, void* stream) {
+    DOTS_REQUIRE(img_hwc && out && H > 0 && W > 0 && rh > 0 && rw > 0, "dots_resize_bicubic_u8: bad arguments");
+    DOTS_REQUIRE(H != rh || W != rw, "dots_resize_bicubic_u8: nothing to do (same size)");
+    DOTS_REQUIRE(W == rw || (xmin_x && xsize_x && w_x && ksize_x > 0 && prec_x > 0), "dots_resize_bicubic_u8: horizontal tap tables missing");
+    DOTS_REQUIRE(H == rh || (xmin_y && xsize_y && w_y && ksize_y > 0 && prec_y > 0), "dots_resize_bicubic_u8: vertical tap tables missing");
+    DOTS_REQUIRE((W == rw || H == rh) || tmp, "dots_resize_bicubic_u8: both axes change: need the [H, rw, 3] intermediate buffer");
+    auto blocks = [](long long total) { return (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16); };
+    const void* src = img_hwc;
+    if (W != rw) {                                       // horizontal pass first (as Pillow / ATen do), uint8 intermediate
+        void* dst = (H != rh) ? tmp : out;
+        const long long total = (long long)H * rw * 3;
+        DOTS_CHECK_CUDA(launch_ex(resample_u8_kernel, dim3(blocks(total)), dim3(256), (size_t)(0), ST(stream), true, (const uint8_t*)src, (uint8_t*)dst,
+                                  (long long)H, W, rw, 3LL, xmin_x, xsize_x, w_x, ksize_x, prec_x));
+        src = dst;
+    }
+    if (H != rh) {
+        const long long total = (long long)rh * rw * 3;
+        DOTS_CHECK_CUDA(launch_ex(resample_u8_kernel, dim3(blocks(total)), dim3(256), (size_t)(0), ST(stream), true, (const uint8_t*)src, (uint8_t*)out,
+                                  1LL, H, rh, (long long)rw * 3, xmin_y, xsize_y, w_y, ksize_y, prec_y));
+    }
+    return 0;
+}
+
 extern "C" int dots_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, long long rows, int cols,
                             float eps, void* stream) {
     DOTS_REQUIRE(rows > 0 && cols % 8 == 0 && cols <= NORM_MAX_CHUNKS * 256 && ldx % 8 == 0 && ldo % 8 == 0,
@@ -723,10 +776,11 @@ extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table
 }
 
 extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed, int batch,
-                                            int H, float eps, void* stream) {
+                                            int H, float eps, int tile_rows, void* stream) {
     DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
+    DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && H % 64 == 0), "dots_decode_residual_rmsnorm: bad tile_rows %d", tile_rows);
     const int threads = ((H / 8) + 31) / 32 * 32;
-    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps));
+    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps, tile_rows));
     return 0;
 }
 

@@ -831,3 +831,26 @@ extern "C" int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_ro
     }
     return bn == 32 ? launch_gemm<32, DOTS_EPI_BF16_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_BF16_T>(ta, tb, p, st);
 }
+
+// Split-K partials over tiled operands: partial[s][b][n] (fp32) = sum over the s-th K slice of X[b, k] * W[n, k]; the 7-kernel decode
+// layer with bulk-copied operands (dots_gemm_skinny_bf16 is the tensor-map version for batches of 65..256).
+extern "C" int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* partial, int batch, int N, int K, int splits, void* stream) {
+    DOTS_REQUIRE(Xt && Wt && partial && batch > 0 && batch <= 64 && N > 0 && K > 0, "dots_decode_gemm_partial: bad arguments batch=%d N=%d K=%d", batch, N, K);
+    GemmParams p{};
+    p.static_is_b = 0;
+    p.M = N; p.N = batch; p.K = K;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    if (splits < 1) splits = 1;
+    if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+    p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+    p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    DOTS_REQUIRE(p.splits == splits, "dots_decode_gemm_partial: splits=%d does not tile %d k-blocks (would use %d)", splits, p.num_k_blocks, p.splits);
+    p.out = partial; p.ldo = N;
+    p.m_blocks = (N + BLOCK_M - 1) / BLOCK_M;
+    p.n_blocks = 1;
+    p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
+    p.b_tiled = reinterpret_cast<const uint8_t*>(Xt);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ta{}, tb{};
+    return batch <= 32 ? launch_gemm<32, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
+}

@@ -170,10 +170,12 @@ class Engine:
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self.launches = 0       # C-ABI kernel launches issued (bench.py reports it)
         self.eos_check_every = 64       # decode steps between looks at the finished flags (only when a stop id is given)
-        # Decode path for batches <= 64: 5 kernels per layer (cluster split-K GEMMs with the reduction, residual add and RMSNorm
-        # on chip; cluster-merged attention) instead of 7 + fp32 partials.  False = the per-op path with
-        # split-K partials and finalize kernels, which also serves batches of 65..256.
-        self.decode_fused = True
+        # Decode layer for batches <= 64:
+        #   "tiled"  7 kernels per layer over pre-tiled operands fetched with bulk copies (split-K partials + finalize kernels)
+        #   "fused"  5 kernels per layer: cluster split-K GEMMs with the reduction, residual add and RMSNorm on chip
+        #   "perop"  7 kernels per layer over row-major operands and tensor-map copies; the only mode for batches of 65..256
+        self.decode_mode = "tiled"
+        self.attn_splits = 0            # 0: planned from the batch size; n: force n key splits in decode attention (tuning runs)
         self._fused_ok: Dict[int, bool] = {}
         self._dec_cache: Optional[dict] = None
         self._cap_stream = torch.cuda.Stream(device=dev)
@@ -182,12 +184,26 @@ class Engine:
     # ------------------------------------------------------------------------------ vision
     @_on_device
     @torch.no_grad()
-    def encode_pages_u8(self, pages, return_layers: bool = False):
-        """ViT forward from uint8 RGB pages already on the device (each [H, W, 3], smart-resized: H, W multiples of 28).
-        The rescale / normalise / patchify half of the HF image processor runs on the GPU (dots_patchify_u8, SURVEY.md
-        section 8f N1), so a page costs 3 B per pixel of host->device traffic instead of 12."""
+    def encode_pages_u8(self, pages, return_layers: bool = False, min_pixels: Optional[int] = None, max_pixels: Optional[int] = None):
+        """ViT forward from uint8 RGB pages [H, W, 3] of ANY size.  The whole image processor runs on the GPU (SURVEY.md section
+        8f N1): smart_resize picks the model size (multiples of 28 inside the pixel budget, image_utils.py:29-63), dots_resize_bicubic_u8
+        resizes bit-identically to the CPU processor, dots_patchify_u8 rescales / normalises / patchifies.  A page costs 3 B per ORIGINAL
+        pixel of host->device traffic instead of 12 B per resized pixel, and no host resize."""
         from .processing import CLIP_MEAN, CLIP_STD
+        from .utils.consts import MIN_PIXELS, MAX_PIXELS
+        from .utils.image_utils import smart_resize
         v = self.cfg.vision
+        f = v.patch_size * v.spatial_merge_size
+        sized = []
+        for pg in pages:
+            pg = pg.to(self.device)
+            H, W = int(pg.shape[0]), int(pg.shape[1])
+            rh, rw = smart_resize(H, W, factor=f, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
+            if (rh, rw) != (H, W):
+                pg = ops.resize_u8(pg.contiguous(), rh, rw)
+                self.launches += (1 if H != rh else 0) + (1 if W != rw else 0)
+            sized.append(pg)
+        pages = sized
         mean255 = (torch.tensor(CLIP_MEAN, dtype=torch.float32) * 255.0).tolist()
         std255 = (torch.tensor(CLIP_STD, dtype=torch.float32) * 255.0).tolist()
         grid = [[1, int(pg.shape[0]) // v.patch_size, int(pg.shape[1]) // v.patch_size] for pg in pages]
@@ -293,15 +309,25 @@ class Engine:
             self.launches += 8
         return x
 
-    def _fused_decode_ok(self, B: int) -> bool:
-        """The cluster GEMMs rendezvous on a device-wide counter: every row-tile cluster of a launch must be resident at once."""
-        if not self.decode_fused or B > 64:
-            return False
-        key = 32 if B <= 32 else 64
-        if key not in self._fused_ok:
-            tiles = -(-self.cfg.text.hidden_size // 128)
-            self._fused_ok[key] = ops.decode_gemm_max_clusters(key) >= tiles
-        return self._fused_ok[key]
+    @property
+    def decode_fused(self) -> bool:
+        return self.decode_mode == "fused"
+
+    @decode_fused.setter
+    def decode_fused(self, on: bool) -> None:
+        self.decode_mode = "fused" if on else "perop"
+
+    def _mode_for(self, B: int) -> str:
+        """The decode-layer variant a batch of B rows runs with."""
+        if B > 64 or self.decode_mode == "perop":
+            return "perop"
+        if self.decode_mode == "fused":
+            # the cluster GEMMs rendezvous on a device-wide counter: every row-tile cluster of a launch must be resident at once
+            key = 32 if B <= 32 else 64
+            if key not in self._fused_ok:
+                self._fused_ok[key] = ops.decode_gemm_max_clusters(key) >= -(-self.cfg.text.hidden_size // 128)
+            return "fused" if self._fused_ok[key] else "tiled"
+        return "tiled"
 
     def _decode_plan(self, B: int):
         t = self.cfg.text
@@ -310,15 +336,15 @@ class Engine:
         kb = lambda k: -(-k // 64)
         tiles = lambda n: -(-n // 128)
         pairs = max(1, B * t.num_key_value_heads)
-        fused = self._fused_decode_ok(B)
-        if fused:
-            # two 103 KB CTAs share an SM: aim for ~2 CTAs per SM; up to 4 key splits merge on chip (cluster), more need the combine kernel
-            attn = max(1, min(16, (2 * self.sms) // pairs))
+        mode = self._mode_for(B)
+        if self.attn_splits:
+            attn = int(self.attn_splits)
         else:
-            # one CTA per (sequence, kv head) once that alone covers most SMs (no combine kernel); flash-decoding splits below
+            # one CTA per (sequence, kv head) once that alone covers most SMs; flash-decoding splits below (<= 4 merge inside a
+            # cluster, more go through the combine kernel)
             attn = 1 if pairs >= (3 * self.sms) // 4 else max(1, min(16, (2 * self.sms) // pairs))
         return dict(
-            fused=fused,
+            mode=mode, fused=(mode == "fused"),
             qkv=ops.pick_splits(tiles(qkv_n), kb(H), self.sms),
             o=ops.pick_splits(tiles(H), kb(t.num_attention_heads * t.head_dim), self.sms),
             gu=ops.pick_splits(tiles(2 * I), kb(H), self.sms),
@@ -330,12 +356,14 @@ class Engine:
         """One greedy step for the whole batch; every call is a C-ABI kernel launch (graph-capturable)."""
         t = self.cfg.text
         nq, nkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
+        H, I = t.hidden_size, t.intermediate_size
+        qkv_n = (nq + 2 * nkv) * hd
         pl = st["plan"]
         scale = hd ** -0.5
         n_layers = len(self.t_layers)
-        if pl["fused"]:
+        B = st["resid"].shape[0]
+        if pl["mode"] == "fused":
             R = st["tile_rows"]
-            H, I = t.hidden_size, t.intermediate_size
             ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps,
                                      counters=st["counters"], tile_rows=R)
             for li, L in enumerate(self.t_layers):
@@ -345,9 +373,24 @@ class Engine:
                                     st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"], out_tile_rows=R)
                 ops.decode_gemm_resnorm(st["attn_t"], L["o_t"], st["resid"], L["ln2"], st["normed_t"], st["stats"][0],
                                         st["counters"][2 * li:2 * li + 1], t.rms_norm_eps, nq * hd)
-                ops.decode_gemm_swiglu(st["normed_t"], L["gu_t"], st["act_t"], st["resid"].shape[0], H)
+                ops.decode_gemm_swiglu(st["normed_t"], L["gu_t"], st["act_t"], B, H)
                 ops.decode_gemm_resnorm(st["act_t"], L["down_t"], st["resid"], nxt, st["normed_t"], st["stats"][1],
                                         st["counters"][2 * li + 1:2 * li + 2], t.rms_norm_eps, I)
+            ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
+        elif pl["mode"] == "tiled":
+            R = st["tile_rows"]
+            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
+            for li, L in enumerate(self.t_layers):
+                nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
+                ops.decode_gemm_partial(st["normed_t"], L["qkv_w_t"], st["partial"], B, qkv_n, H, pl["qkv"])
+                ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
+                                      st["ctx_len"], st["attn_t"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"],
+                                      out_tile_rows=R)
+                ops.decode_gemm_partial(st["attn_t"], L["o_t"], st["partial"], B, H, nq * hd, pl["o"])
+                ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
+                ops.decode_gemm_swiglu(st["normed_t"], L["gu_t"], st["act_t"], B, H)
+                ops.decode_gemm_partial(st["act_t"], L["down_t"], st["partial"], B, H, I, pl["down"])
+                ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed_t"], t.rms_norm_eps, tile_rows=R)
             ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
         else:
             ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
@@ -391,8 +434,8 @@ class Engine:
         st["finished"] = torch.zeros(B, device=dev, dtype=torch.int32)
         st["forced"] = forced_ids.to(dev).long().contiguous() if forced_ids is not None else None
         st["qkv"] = torch.empty((B, (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim), device=dev, dtype=torch.bfloat16)
-        if pl["fused"]:
-            # k-block-tiled activation buffers of the bulk-copy decode path (rows beyond the batch stay zero)
+        if pl["mode"] != "perop":
+            # k-block-tiled activation buffers of the bulk-copy decode paths (rows beyond the batch stay zero)
             R = st["tile_rows"] = ops.decode_tile_rows(B)
             tiled = lambda k: torch.zeros(-(-k // 64) * R * 64, device=dev, dtype=torch.bfloat16)
             st["normed_t"], st["attn_t"], st["act_t"] = tiled(H), tiled(t.num_attention_heads * t.head_dim), tiled(t.intermediate_size)
@@ -420,10 +463,8 @@ class Engine:
 
     def launches_per_decode_step(self, B: int) -> int:
         pl = self._decode_plan(B)
-        if pl["fused"]:
-            per_layer = 5 + (1 if pl["attn"] > ops.ATTN_DECODE_MAX_CLUSTER else 0)
-        else:
-            per_layer = 7 + (1 if pl["attn"] > 1 and not (ops.DECODE_CLUSTER and pl["attn"] <= ops.ATTN_DECODE_MAX_CLUSTER) else 0)
+        combine = 1 if pl["attn"] > 1 and not (ops.DECODE_CLUSTER and pl["attn"] <= ops.ATTN_DECODE_MAX_CLUSTER) else 0
+        per_layer = (5 if pl["mode"] == "fused" else 7) + combine
         return 1 + per_layer * len(self.t_layers) + 2
 
     @_on_device
@@ -432,7 +473,7 @@ class Engine:
                  pixel_values: Optional[torch.Tensor] = None, image_grid_thw=None, max_new_tokens: int = 16,
                  eos_token_id=None, pad_token_id: int = 0, forced_ids: Optional[torch.Tensor] = None,
                  return_logits: bool = False, use_graph: bool = True, image_embeds: Optional[torch.Tensor] = None,
-                 pages_u8=None, **unused) -> GenerateOutput:
+                 pages_u8=None, min_pixels: Optional[int] = None, max_pixels: Optional[int] = None, **unused) -> GenerateOutput:
         """HF-shaped greedy generation: returns ids [B, T + N'] including the prompt (parser.py:110-113)."""
         t = self.cfg.text
         dev = self.device
@@ -455,7 +496,7 @@ class Engine:
         cu[1:] = lens.cumsum(0).to(torch.int32)
 
         if image_embeds is None and pages_u8 is not None:
-            image_embeds = self.encode_pages_u8(pages_u8)          # GPU half of the image processor (uint8 pages in)
+            image_embeds = self.encode_pages_u8(pages_u8, min_pixels=min_pixels, max_pixels=max_pixels)    # the image processor on the GPU
         elif image_embeds is None and pixel_values is not None:
             image_embeds = self.encode_images(pixel_values, image_grid_thw)
         slots = None
@@ -469,7 +510,7 @@ class Engine:
         # KV cache, decode workspaces and the captured decode graph are kept from call to call when the shape key repeats
         # (a serving loop and the benchmark call generate with the same batch geometry over and over)
         stops_key = tuple(stop_list(eos_token_id)[: ops.MAX_STOP_IDS])
-        key = (B, ctx_max, N, stops_key, int(pad_token_id), bool(self.decode_fused), ops.DECODE_CLUSTER)
+        key = (B, ctx_max, N, stops_key, int(pad_token_id), self.decode_mode, self.attn_splits, ops.DECODE_CLUSTER)
         ent = self._dec_cache if (self._dec_cache is not None and self._dec_cache["key"] == key and forced_ids is None) else None
         if ent is None:
             self._dec_cache = None                      # release the previous geometry's buffers before allocating new ones

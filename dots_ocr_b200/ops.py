@@ -185,9 +185,10 @@ def attn_decode(q, k_cache, v_cache, ctx_len, out, n_q_heads: int, n_kv_heads: i
 
 
 def attn_decode_fused(partial, qkv_splits: int, bias, pos, inv_freq, k_cache, v_cache, ctx_len, out, n_q_heads: int,
-                      n_kv_heads: int, ctx_max: int, n_splits: int, scale: float, part_o=None, part_ml=None, head_dim: int = 128):
+                      n_kv_heads: int, ctx_max: int, n_splits: int, scale: float, part_o=None, part_ml=None, head_dim: int = 128,
+                      out_tile_rows: int = 0):
     """QKV finalize (split-K reduce + bias + RoPE + KV append) fused into the decode attention kernel."""
-    B = out.shape[0]
+    B = ctx_len.numel()
     assert ctx_len.dtype == torch.int32 and pos.dtype == torch.int32 and partial.dtype == torch.float32
     if n_splits > 1:
         if part_o is None:
@@ -195,7 +196,7 @@ def attn_decode_fused(partial, qkv_splits: int, bias, pos, inv_freq, k_cache, v_
         if part_ml is None:
             part_ml = torch.empty((B, n_q_heads, n_splits, 2), device=out.device, dtype=torch.float32)
     rc = _lib.load().dots_attn_decode_fused(_p(partial), qkv_splits, _p(bias), _p(pos), _p(inv_freq), _p(k_cache), _p(v_cache),
-                                            _p(ctx_len), _p(out), _p(part_o), _p(part_ml), B, n_q_heads, n_kv_heads, head_dim,
+                                            _p(ctx_len), _p(out), int(out_tile_rows), _p(part_o), _p(part_ml), B, n_q_heads, n_kv_heads, head_dim,
                                             _ll(ctx_max), n_splits, C.c_float(scale), _stream())
     _lib.check(rc, "dots_attn_decode_fused")
     return out
@@ -223,6 +224,38 @@ def patchify_u8(img: torch.Tensor, patch: int, merge: int, mean255, std255, ldo:
     sd = (C.c_float * 3)(*[float(v) for v in std255])
     rc = _lib.load().dots_patchify_u8(_p(img), H, W, patch, merge, m, sd, _p(out), ldo, _stream())
     _lib.check(rc, "dots_patchify_u8")
+    return out
+
+
+_RESIZE_TABLES = {}
+
+
+def _resize_tables(in_size: int, out_size: int, device):
+    """Device copies of one axis's tap tables (dots_ocr_b200/resize.py), cached per (in, out, device)."""
+    key = (in_size, out_size, str(device))
+    t = _RESIZE_TABLES.get(key)
+    if t is None:
+        from .resize import axis_tables
+        lo, n, w, prec = axis_tables(in_size, out_size)
+        t = (torch.from_numpy(lo).to(device), torch.from_numpy(n).to(device), torch.from_numpy(w).to(device), int(w.shape[1]), int(prec))
+        if len(_RESIZE_TABLES) < 512:
+            _RESIZE_TABLES[key] = t
+    return t
+
+
+def resize_u8(img: torch.Tensor, rh: int, rw: int) -> torch.Tensor:
+    """uint8 HWC page on the device -> [rh, rw, 3], bicubic + antialias, bit-identical to the CPU image processor's resize."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
+    H, W = int(img.shape[0]), int(img.shape[1])
+    if (H, W) == (rh, rw):
+        return img
+    out = torch.empty((rh, rw, 3), device=img.device, dtype=torch.uint8)
+    tmp = torch.empty((H, rw, 3), device=img.device, dtype=torch.uint8) if (H != rh and W != rw) else None
+    tx = _resize_tables(W, rw, img.device) if W != rw else (None, None, None, 0, 0)
+    ty = _resize_tables(H, rh, img.device) if H != rh else (None, None, None, 0, 0)
+    rc = _lib.load().dots_resize_bicubic_u8(_p(img), H, W, _p(tmp), _p(out), rh, rw, _p(tx[0]), _p(tx[1]), _p(tx[2]), tx[3], tx[4],
+                                            _p(ty[0]), _p(ty[1]), _p(ty[2]), ty[3], ty[4], _stream())
+    _lib.check(rc, "dots_resize_bicubic_u8")
     return out
 
 
@@ -372,6 +405,15 @@ def decode_gemm_resnorm(xt: torch.Tensor, wt: torch.Tensor, resid: torch.Tensor,
     _lib.check(rc, "dots_decode_gemm_resnorm")
 
 
+def decode_gemm_partial(xt: torch.Tensor, wt: torch.Tensor, partial: torch.Tensor, batch: int, N: int, K: int, splits: int) -> torch.Tensor:
+    """Split-K partials [splits, batch, N] fp32 over tiled operands (gemm_skinny with bulk-copied operands)."""
+    _tiled_act_ok(xt, batch, K, "xt"); _tiled_w_ok(wt, N, K, "wt")
+    assert partial.dtype == torch.float32 and partial.is_contiguous() and partial.numel() >= splits * batch * N
+    rc = _lib.load().dots_decode_gemm_partial(_p(xt), _p(wt), _p(partial), batch, N, K, splits, _stream())
+    _lib.check(rc, "dots_decode_gemm_partial")
+    return partial
+
+
 def decode_gemm_swiglu(xt: torch.Tensor, wt: torch.Tensor, act_t: torch.Tensor, batch: int, K: int) -> torch.Tensor:
     """gate|up + SwiGLU of a decode step over tiled operands; act_t (k-block-tiled [batch, I]) is the B operand of down_proj."""
     two_i = wt.shape[0] * 128
@@ -435,9 +477,9 @@ def debug_set_fault(code: int) -> None:
     _lib.check(_lib.load().dots_debug_set_fault(int(code)), "dots_debug_set_fault")
 
 
-def decode_residual_rmsnorm(partial, splits, resid, w, normed, eps):
+def decode_residual_rmsnorm(partial, splits, resid, w, normed, eps, tile_rows: int = 0):
     B, H = resid.shape
-    rc = _lib.load().dots_decode_residual_rmsnorm(_p(partial), splits, _p(resid), _p(w), _p(normed), B, H, C.c_float(eps), _stream())
+    rc = _lib.load().dots_decode_residual_rmsnorm(_p(partial), splits, _p(resid), _p(w), _p(normed), B, H, C.c_float(eps), int(tile_rows), _stream())
     _lib.check(rc, "dots_decode_residual_rmsnorm")
 
 

@@ -80,6 +80,22 @@ def preprocess_image_u8(image, min_pixels: Optional[int] = None, max_pixels: Opt
     return img.contiguous()
 
 
+def page_to_u8(image) -> torch.Tensor:
+    """PIL image (any mode) or uint8 HWC array -> uint8 HWC RGB tensor at its ORIGINAL size (alpha composited on white like the
+    reference, image_utils.py:74-80).  Everything after this -- resize, rescale, normalise, patchify -- runs on the GPU."""
+    if not isinstance(image, (np.ndarray, torch.Tensor)):
+        image = np.asarray(to_rgb(image))
+    img = torch.from_numpy(np.array(image, copy=True)) if not isinstance(image, torch.Tensor) else image
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3, "expect uint8 HWC RGB"
+    return img.contiguous()
+
+
+def model_image_tokens(h: int, w: int, min_pixels: Optional[int] = None, max_pixels: Optional[int] = None, patch: int = 14, merge: int = 2) -> int:
+    """<|imgpad|> slots a page of h x w pixels occupies after smart_resize (image tokens = patches / merge^2)."""
+    rh, rw = smart_resize(h, w, factor=patch * merge, min_pixels=min_pixels or MIN_PIXELS, max_pixels=max_pixels or MAX_PIXELS)
+    return (rh // patch) * (rw // patch) // (merge * merge)
+
+
 class SyntheticTokenizer:
     """Byte-level stand-in (ids 0..255 = bytes) with the three image specials mapped onto the config's
     reserved ids.  NOT the dots.ocr tokenizer: decoded text is meaningless with synthetic weights."""

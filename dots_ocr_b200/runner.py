@@ -59,18 +59,21 @@ class PageRunner:
 
     def infer_batch(self, images: Sequence, prompts: Sequence[str], max_new_tokens: int = 512, gpu_preprocess: bool = True,
                     budgets: Optional[Sequence[int]] = None) -> List[str]:
-        """gpu_preprocess: resize on the host (uint8), rescale / normalise / patchify on the GPU (3 B per pixel over PCIe instead of
+        """gpu_preprocess: the whole image processor (resize, rescale / normalise / patchify) on the GPU (3 B per pixel over PCIe instead of
         12); False = the reference's host processor output (fp32 pixel_values) as `generate` input."""
         n_new = max(1, min(int(max_new_tokens), self.cap))
         if gpu_preprocess:
-            from .processing import preprocess_image_u8, build_text_inputs
-            pages = [preprocess_image_u8(im, self.min_pixels, self.max_pixels) for im in images]
-            inputs = build_text_inputs(self.tokenizer, [(p.shape[0] // 14) * (p.shape[1] // 14) // 4 for p in pages], prompts)
+            # host: RGB conversion only; resize + rescale + normalise + patchify run on the GPU (bit-identical to the CPU processor)
+            from .processing import page_to_u8, model_image_tokens, build_text_inputs
+            pages = [page_to_u8(im) for im in images]
+            inputs = build_text_inputs(self.tokenizer, [model_image_tokens(int(p.shape[0]), int(p.shape[1]), self.min_pixels, self.max_pixels)
+                                                        for p in pages], prompts)
         else:
             inputs = build_inputs(self.tokenizer, images, prompts, self.min_pixels, self.max_pixels)
         with self._lock:
             dev = self.engine.device
-            kw = dict(pages_u8=[p.to(dev, non_blocking=True) for p in pages]) if gpu_preprocess else \
+            kw = dict(pages_u8=[p.pin_memory().to(dev, non_blocking=True) for p in pages], min_pixels=self.min_pixels, max_pixels=self.max_pixels) \
+                if gpu_preprocess else \
                 dict(pixel_values=inputs["pixel_values"].to(dev), image_grid_thw=inputs["image_grid_thw"])
             # every stop id of the checkpoint's generation config when the tokenizer knows them (HF accepts a list too)
             stops = list(getattr(self.tokenizer, "stop_ids", ())) or self.tokenizer.eos_token_id

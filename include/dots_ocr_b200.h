@@ -109,11 +109,12 @@ DOTS_API int dots_attn_decode(const void* q, const void* k_cache, const void* v_
 /* dots_attn_decode with the QKV finalize fused in front: the current token's q/k/v arrive as the split-K fp32 partials
  * qkv_partial [qkv_splits][batch][(n_q_heads + 2 n_kv_heads) * 128] of dots_gemm_skinny_bf16; the kernel reduces them in split
  * order, adds qkv_bias, applies HF's bf16 RoPE at pos[b] ([Q]:102-146), appends k, v at cache[b, :, pos[b]]
- * (cache_utils.py:119-120) and attends with q held in shared memory.  Requires ctx_len[b] == pos[b] + 1. */
+ * (cache_utils.py:119-120) and attends with q held in shared memory.  Requires ctx_len[b] == pos[b] + 1.
+ * out_tile_rows > 0: `out` is written k-block-tiled with that many rows per tile (see the decode-projection section); 0: row-major. */
 DOTS_API int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, const void* qkv_bias, const int* pos,
                            const float* inv_freq, void* k_cache, void* v_cache, const int* ctx_len, void* out,
-                           float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads, int head_dim,
-                           long long ctx_max, int n_splits, float softmax_scale, void* stream);
+                           int out_tile_rows, float* part_o, float* part_ml, int batch, int n_q_heads, int n_kv_heads,
+                           int head_dim, long long ctx_max, int n_splits, float softmax_scale, void* stream);
 
 /* dots_attn_decode_fused with the current token's q|k|v as the bf16 row [batch][(n_q_heads + 2 n_kv_heads) * 128] written by
  * dots_decode_gemm_qkv (bias already added): RoPE at pos[b] + KV append + attention.  out_tile_rows > 0: `out` is written in the
@@ -142,6 +143,15 @@ DOTS_API int dots_cast_pad_bf16(const void* in, int in_is_bf16, long long rows, 
  * followed by dots_cast_pad_bf16 ([C] image_processing_qwen2_vl.py:148-232). */
 DOTS_API int dots_patchify_u8(const void* img_hwc, int H, int W, int patch, int merge, const float* mean255, const float* std255,
                      void* out, int ldo, void* stream);
+
+/* Page resize on the GPU: uint8 RGB [H, W, 3] -> [rh, rw, 3], bicubic + antialias, bit-identical to the resize of the stock image
+ * processor (torchvision resize on uint8 = Pillow's integer algorithm; [C] image_processing_qwen2_vl.py:148-232; reference entry
+ * dots_ocr/utils/image_utils.py:116-138).  Horizontal pass then vertical pass with a uint8 intermediate `tmp` [H, rw, 3] (needed only
+ * when both axes change).  Tap tables per axis are DEVICE arrays built by dots_ocr_b200/resize.py: xmin / xsize [out] int32, w [out,
+ * ksize] int16 fixed point with `prec` fractional bits. */
+DOTS_API int dots_resize_bicubic_u8(const void* img_hwc, int H, int W, void* tmp, void* out, int rh, int rw, const int* xmin_x,
+                           const int* xsize_x, const short* w_x, int ksize_x, int prec_x, const int* xmin_y, const int* xsize_y,
+                           const short* w_y, int ksize_y, int prec_y, void* stream);
 
 /* RMSNorm, fp32 statistics: out = bf16(bf16(x * rsqrt(mean x^2 + eps)) * w)   ([Q]:258-263, [V]:450,456,518). */
 DOTS_API int dots_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, long long rows, int cols,
@@ -195,8 +205,9 @@ DOTS_API int dots_argmax_advance(const void* logits, long long ldl, int batch, i
 DOTS_API int dots_decode_embed_rmsnorm(const long long* ids, const void* table, long long vocab, const void* w, void* resid,
                               void* normed, int batch, int H, float eps, unsigned int* counters, int n_counters, int tile_rows,
                               void* stream);
+/* tile_rows > 0: normed is written k-block-tiled (rows per tile); 0: row-major. */
 DOTS_API int dots_decode_residual_rmsnorm(const float* partial, int splits, void* resid, const void* w, void* normed,
-                                 int batch, int H, float eps, void* stream);
+                                 int batch, int H, float eps, int tile_rows, void* stream);
 DOTS_API int dots_decode_qkv_rope_append(const float* partial, int splits, const void* bias, const int* pos,
                                 const float* inv_freq, void* q_out, void* k_cache, void* v_cache, long long ctx_max,
                                 int batch, int n_q_heads, int n_kv_heads, int head_dim, void* stream);
@@ -227,6 +238,9 @@ DOTS_API int dots_decode_gemm_resnorm(const void* Xt, const void* Wt, void* resi
 /* gate|up projection + SwiGLU of one decode step, batch <= 64 (no split-K: 2I/128 tiles cover the SMs).  Wt = tiled interleaved
  * gate|up weight [2I, K] (as DOTS_EPI_SWIGLU); act_t [batch, I] = bf16(bf16(silu(bf16 g)) * bf16 u), written k-block-tiled. */
 DOTS_API int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act_t, int batch, int two_i, int K, void* stream);
+
+/* Split-K partials over tiled operands: partial[s][b][n] fp32 (dots_gemm_skinny_bf16 with bulk-copied operands). */
+DOTS_API int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* partial, int batch, int N, int K, int splits, void* stream);
 
 /* lm_head of one decode step, batch <= 64: out[b, n] = bf16(X . W^T), row-major.  x_tile_rows = 32 / 64: X is k-block-tiled;
  * x_tile_rows = 0: X is row-major with pitch ldx (first token after prefill). */

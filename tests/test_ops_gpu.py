@@ -450,3 +450,35 @@ def test_patchify_u8_matches_host_processor(H, W):
     got = ops.patchify_u8(img.to(DEV), 14, 2, mean255, std255, 640)
     assert got.shape == ref.shape
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("H,W,rh,rw", [(64, 80, 56, 84), (1024, 1024, 1036, 1036), (300, 200, 140, 84), (257, 311, 252, 308), (90, 64, 90, 56),
+                                       (61, 70, 56, 70), (2250, 1700, 2240, 1708)])
+def test_resize_bicubic_u8_equals_the_cpu_processor(H, W, rh, rw):
+    """dots_resize_bicubic_u8 == torchvision's uint8 bicubic + antialias resize (the stock image processor's), bit for bit."""
+    import torchvision.transforms.v2.functional as tvF
+    from torchvision.transforms import InterpolationMode
+    ops = _ops()
+    g = torch.Generator().manual_seed(H + W)
+    img = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+    ref = tvF.resize(img.permute(2, 0, 1).contiguous(), [rh, rw], interpolation=InterpolationMode.BICUBIC, antialias=True).permute(1, 2, 0)
+    got = ops.resize_u8(img.to(DEV), rh, rw).cpu()
+    assert torch.equal(got, ref.contiguous())
+
+
+def test_gpu_image_processor_equals_host_processor():
+    """Raw uint8 page of arbitrary size -> resize + rescale + normalise + patchify on the GPU == processing.preprocess_image on the host
+    followed by the bf16 cast (the pixel_values the ViT's patch-embed GEMM consumes), bit for bit."""
+    from dots_ocr_b200 import config, weights
+    from dots_ocr_b200.engine import Engine
+    from dots_ocr_b200.processing import preprocess_image
+    ops = _ops()
+    cfg = config.tiny()
+    eng = Engine(cfg, weights.make_synthetic_checkpoint(cfg, 0, "random"), DEV)
+    g = torch.Generator().manual_seed(3)
+    for (H, W) in [(100, 130), (224, 112), (75, 300)]:
+        img = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+        pv, grid = preprocess_image(img.numpy())
+        a = eng.encode_images(pv.to(DEV), grid)
+        b = eng.encode_pages_u8([img.to(DEV)])
+        assert torch.equal(a, b), (H, W)

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dots_ocr_b200 import config, weights, ops  # noqa: E402
 from dots_ocr_b200.engine import Engine  # noqa: E402
 
-OPS = ("gemm_skinny", "gemm_skinny_swiglu", "attn_decode_fused", "attn_decode_qkv", "decode_residual_rmsnorm", "decode_embed_rmsnorm",
+OPS = ("decode_gemm_partial", "decode_gemm_swiglu", "decode_gemm_head", "gemm_skinny", "gemm_skinny_swiglu", "attn_decode_fused", "attn_decode_qkv", "decode_residual_rmsnorm", "decode_embed_rmsnorm",
        "argmax_advance", "decode_gemm_qkv", "decode_gemm_resnorm")
 
 
@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ctx", type=int, default=1881)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--fused", type=int, default=1, help="1: 5-kernel layer (cluster GEMMs), 0: 7-kernel per-op layer")
+    ap.add_argument("--mode", default="tiled", choices=["tiled", "fused", "perop"], help="decode layer variant (Engine.decode_mode)")
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="override the flash-decoding split count of the plan")
     ap.add_argument("--no-cluster", action="store_true", help="combine kernel instead of the cluster merge for 2..4 attention splits")
     ap.add_argument("--quick", action="store_true", help="only the full step and the attention ablation")
@@ -33,7 +33,7 @@ def main():
     cfg = config.full()
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev)
     eng = Engine(cfg, ck, dev)
-    eng.decode_fused = bool(args.fused)
+    eng.decode_mode = args.mode
     del ck
     if args.no_cluster:
         ops.set_decode_cluster(False)
@@ -42,9 +42,7 @@ def main():
     kc, vc = eng._alloc_cache(B, ctx_max)
     kc.normal_(); vc.normal_()
     lens = torch.full((B,), args.ctx, device=dev, dtype=torch.int64)
-    if args.attn_splits:
-        plan0 = eng._decode_plan
-        eng._decode_plan = lambda b: dict(plan0(b), attn=args.attn_splits)
+    eng.attn_splits = args.attn_splits
     real = {n: getattr(ops, n) for n in OPS}
     t = cfg.text
     H, I = t.hidden_size, t.intermediate_size
@@ -60,7 +58,7 @@ def main():
             if shape is None:
                 setattr(ops, n, lambda *a, **k: None)
             else:
-                def filt(*a, _o=real[n], _s=shape, **k):
+                def filt(*a, _o=real[n], _s=tuple(shape), **k):
                     if tuple(a[1].shape) == _s:
                         return None
                     return _o(*a, **k)
@@ -86,16 +84,25 @@ def main():
 
     full = run()
     pl = eng._decode_plan(B)
+    L0 = eng.t_layers[0]
     res = {"full_ms": round(full, 4), "plan": {k: v for k, v in pl.items()}}
-    if pl["fused"]:
+    if pl["mode"] == "fused":
         cases = [("attention(+rope, append)", [("attn_decode_qkv", None)]),
                  ("qkv gemm (cluster)", [("decode_gemm_qkv", None)]),
-                 ("o gemm + residual + norm (cluster)", [("decode_gemm_resnorm", (H, H))]),
-                 ("down gemm + residual + norm (cluster)", [("decode_gemm_resnorm", (H, I))]),
-                 ("gate|up gemm + swiglu", [("gemm_skinny_swiglu", None)]),
-                 ("lm_head gemm", [("gemm_skinny", (t.vocab_size, H))]),
+                 ("o gemm + residual + norm (cluster)", [("decode_gemm_resnorm", L0["o_t"].shape)]),
+                 ("down gemm + residual + norm (cluster)", [("decode_gemm_resnorm", L0["down_t"].shape)]),
+                 ("gate|up gemm + swiglu", [("decode_gemm_swiglu", None)]),
+                 ("lm_head gemm", [("decode_gemm_head", None)]),
                  ("argmax", [("argmax_advance", None)]),
-                 ("all gemms", [("decode_gemm_qkv", None), ("decode_gemm_resnorm", None), ("gemm_skinny_swiglu", None), ("gemm_skinny", None)])]
+                 ("all gemms", [("decode_gemm_qkv", None), ("decode_gemm_resnorm", None), ("decode_gemm_swiglu", None), ("decode_gemm_head", None)])]
+    elif pl["mode"] == "tiled":
+        cases = [("attention(+qkv finalize)", [("attn_decode_fused", None)]),
+                 ("qkv gemm", [("decode_gemm_partial", L0["qkv_w_t"].shape)]), ("o gemm", [("decode_gemm_partial", L0["o_t"].shape)]),
+                 ("down gemm", [("decode_gemm_partial", L0["down_t"].shape)]), ("lm_head gemm", [("decode_gemm_head", None)]),
+                 ("gate|up gemm + swiglu", [("decode_gemm_swiglu", None)]),
+                 ("residual+rmsnorm finalize", [("decode_residual_rmsnorm", None)]),
+                 ("argmax", [("argmax_advance", None)]),
+                 ("all gemms", [("decode_gemm_partial", None), ("decode_gemm_swiglu", None), ("decode_gemm_head", None)])]
     else:
         cases = [("attention(+qkv finalize)", [("attn_decode_fused", None)]),
                  ("qkv gemm", [("gemm_skinny", (qkv_n, H))]), ("o gemm", [("gemm_skinny", (H, H))]),

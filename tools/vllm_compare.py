@@ -1,9 +1,7 @@
 #!/usr/bin/env python
 """On-box comparison against the in-image vLLM ``DotsOCRForCausalLM`` on the SAME synthetic parameters.
 
-NOT RUN YET: written after round 1's GPU budget was spent; the host-side pieces it leans on (fabricated checkpoint
-directory, HFTokenizer, PageRunner.from_checkpoint) are covered by tests/test_checkpoint_cpu.py.  First thing to run in
-round 2:
+Results: profiles/vllm_compare_r2.md.
 
     python tools/make_checkpoint_dir.py --preset full --flavour peaked --out /tmp/dots_full
     python tools/vllm_compare.py --dir /tmp/dots_full --impl vllm --pages 64 --new-tokens 512 > gpurun_out/vllm.json
@@ -62,17 +60,17 @@ def run_vllm(a) -> dict:
 
 def run_ours(a) -> dict:
     import torch
-    from dots_ocr_b200.processing import build_text_inputs, preprocess_image_u8
+    from dots_ocr_b200.processing import build_text_inputs, page_to_u8, model_image_tokens
     from dots_ocr_b200.runner import PageRunner
     runner = PageRunner.from_checkpoint(a.dir, device="cuda:0")
     eng, tk = runner.engine, runner.tokenizer
     imgs = pages(a.pages, a.side)
 
     def once(batch, n_new):
-        pg = [preprocess_image_u8(im) for im in batch]
-        inp = build_text_inputs(tk, [(p.shape[0] // 14) * (p.shape[1] // 14) // 4 for p in pg], [PROMPT] * len(batch))
+        pg = [page_to_u8(im) for im in batch]                 # RGB bytes at the original size; resize + normalise + patchify on the GPU
+        inp = build_text_inputs(tk, [model_image_tokens(int(p.shape[0]), int(p.shape[1])) for p in pg], [PROMPT] * len(batch))
         out = eng.generate(input_ids=inp["input_ids"].to(eng.device), attention_mask=inp["attention_mask"].to(eng.device),
-                           pages_u8=[p.to(eng.device, non_blocking=True) for p in pg], max_new_tokens=n_new,
+                           pages_u8=[p.pin_memory().to(eng.device, non_blocking=True) for p in pg], max_new_tokens=n_new,
                            eos_token_id=None, pad_token_id=tk.pad_token_id)
         T = inp["input_ids"].shape[1]
         return out.sequences[:, T:].cpu()
