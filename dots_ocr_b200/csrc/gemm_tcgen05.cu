@@ -35,6 +35,10 @@ struct GemmParams {
     const uint8_t* a_tiled;        // ops.tile_weight(W): [m_blocks][num_k_blocks] blobs of 16 KB; nullptr: tmap_a
     const uint8_t* b_tiled;        // activations, k-block-tiled with BLOCK_N rows per tile (ops.tile_rows); nullptr: tmap_b
     int out_tiled;                 // SWIGLU_T: act is written k-block-tiled with BLOCK_N rows per tile (B operand of down_proj)
+    // DOTS_EPI_ROPE: 2-D rotary embedding of the ViT fused into the q|k|v projection (columns < rope_cols are q and k heads)
+    const float* rope_cos;         // [M, 64] fp32
+    const float* rope_sin;
+    int rope_cols;
 };
 
 constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
@@ -102,6 +106,47 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int row,
                 for (int q = 0; q < 4; ++q)
                     if (col + q * 8 + 8 <= p.N / 2)
                         *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            }
+        }
+    } else if constexpr (EPI == DOTS_EPI_ROPE) {
+        // ViT q|k|v projection with the 2-D rotary embedding fused ([V]:287 + :295-302): an epilogue group owns one 128-column head;
+        // q = bf16(acc) first (the Linear's output dtype), then NeoX rotate-half in fp32 with one rounding -- the arithmetic of
+        // vit_rope_apply_kernel, so the result is bit-identical to GEMM + that kernel, without the extra read-modify-write pass.
+        static_assert(EPI != DOTS_EPI_ROPE || BLOCK_N == 256, "rope epilogue needs 256-wide tiles (one head per epilogue group)");
+        bf16* out = reinterpret_cast<bf16*>(p.out);
+        const int col_head = n_blk * BLOCK_N + eg * 128;
+        const bool rot = col_head < p.rope_cols;
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t a[32], b[32];
+            tmem_ld_32x32b_x32(t_row + eg * 128 + half * 32, a);
+            tmem_ld_32x32b_x32(t_row + eg * 128 + 64 + half * 32, b);
+            tmem_ld_wait();
+            if (!row_ok || col_head + 128 > p.N) continue;
+            bf16* dst = out + (long long)row * p.ldo + col_head + half * 32;
+            const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + (long long)row * 64 + half * 32);
+            const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + (long long)row * 64 + half * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float x1[8], x2[8], o1[8], o2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { x1[j] = bf16_round(__uint_as_float(a[q * 8 + j])); x2[j] = bf16_round(__uint_as_float(b[q * 8 + j])); }
+                if (rot) {
+                    float c[8], sn[8];
+                    *reinterpret_cast<float4*>(c) = __ldg(cp + 2 * q); *reinterpret_cast<float4*>(c + 4) = __ldg(cp + 2 * q + 1);
+                    *reinterpret_cast<float4*>(sn) = __ldg(sp + 2 * q); *reinterpret_cast<float4*>(sn + 4) = __ldg(sp + 2 * q + 1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        o1[j] = __fsub_rn(__fmul_rn(x1[j], c[j]), __fmul_rn(x2[j], sn[j]));
+                        o2[j] = __fadd_rn(__fmul_rn(x2[j], c[j]), __fmul_rn(x1[j], sn[j]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { o1[j] = x1[j]; o2[j] = x2[j]; }
+                }
+                *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(pack_bf16x2(o1[0], o1[1]), pack_bf16x2(o1[2], o1[3]), pack_bf16x2(o1[4], o1[5]), pack_bf16x2(o1[6], o1[7]));
+                *reinterpret_cast<uint4*>(dst + 64 + q * 8) = make_uint4(pack_bf16x2(o2[0], o2[1]), pack_bf16x2(o2[2], o2[3]), pack_bf16x2(o2[4], o2[5]), pack_bf16x2(o2[6], o2[7]));
             }
         }
     } else if constexpr (EPI == DOTS_EPI_SWIGLU_T) {
@@ -615,9 +660,11 @@ extern "C" int dots_set_gemm_pair(int enable) {
     return 0;
 }
 
-extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
-                              int M, int N, int K, int epilogue, const void* bias, const void* residual,
-                              long long ldr, void* stream) {
+extern "C" int dots_vit_rope_apply(void* qkv, long long ld, int S, int heads, int head_dim, const float* cos_t, const float* sin_t, void* stream);
+
+static int gemm_bf16_impl(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                          int M, int N, int K, int epilogue, const void* bias, const void* residual,
+                          long long ldr, const float* rope_cos, const float* rope_sin, int rope_cols, void* stream) {
     DOTS_REQUIRE(M > 0 && N > 0 && K > 0, "dots_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
     DOTS_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && N % 8 == 0,
                  "dots_gemm_bf16: K, N and all pitches must be multiples of 8 (16-byte TMA/vector alignment)");
@@ -634,12 +681,23 @@ extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long 
     p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
     p.kb_per_split = p.num_k_blocks;
     p.m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.rope_cols = rope_cols;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta, tb;
     if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M)) return -4;
 
     // CTA-pair kernel (256 x 256 tiles) for problems with at least two waves of such tiles
     const bool pair_ok = g_gemm_pair && (N % 256 == 0) && ((long long)((M + 255) / 256) * (N / 256) >= num_sms());
+    if (epilogue == DOTS_EPI_ROPE) {
+        DOTS_REQUIRE(rope_cos && rope_sin && rope_cols % 256 == 0 && rope_cols <= N && N % 128 == 0,
+                     "dots_gemm_bf16_rope: need cos/sin tables, rope_cols %% 256 == 0 (q and k heads of 128), N %% 128 == 0");
+        const long long tiles256 = (long long)p.m_blocks * ((N + 255) / 256);
+        if (!(N % 256 == 0 && (pair_ok || tiles256 >= 2LL * num_sms()))) {
+            // small problems run on 128-wide tiles, where a head straddles two epilogue groups: plain store, then the rotary pass
+            if (int rc = gemm_bf16_impl(A, lda, W, ldw, out, ldo, M, N, K, DOTS_EPI_STORE, nullptr, nullptr, 0, nullptr, nullptr, 0, stream)) return rc;
+            return dots_vit_rope_apply(out, ldo, M, rope_cols / 256, 128, rope_cos, rope_sin, stream);
+        }
+    }
     if (pair_ok && epilogue != DOTS_EPI_F32_PARTIAL_T && epilogue != DOTS_EPI_BF16_T && epilogue != DOTS_EPI_SWIGLU_T) {
         if ((epilogue == DOTS_EPI_BIAS || epilogue == DOTS_EPI_BIAS_GELU) && !bias) {
             set_error("dots_gemm_bf16: bias epilogue without bias pointer");
@@ -658,6 +716,7 @@ extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long 
             case DOTS_EPI_BIAS_GELU: return launch_gemm2<DOTS_EPI_BIAS_GELU>(ta, tb2, p, st);
             case DOTS_EPI_RESIDUAL: return launch_gemm2<DOTS_EPI_RESIDUAL>(ta, tb2, p, st);
             case DOTS_EPI_SWIGLU: return launch_gemm2<DOTS_EPI_SWIGLU>(ta, tb2, p, st);
+            case DOTS_EPI_ROPE: return launch_gemm2<DOTS_EPI_ROPE>(ta, tb2, p, st);
         }
     }
 
@@ -685,6 +744,7 @@ extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long 
             case DOTS_EPI_BIAS: return launch_gemm<256, DOTS_EPI_BIAS>(ta, tb, p, st);
             case DOTS_EPI_BIAS_GELU: return launch_gemm<256, DOTS_EPI_BIAS_GELU>(ta, tb, p, st);
             case DOTS_EPI_RESIDUAL: return launch_gemm<256, DOTS_EPI_RESIDUAL>(ta, tb, p, st);
+            case DOTS_EPI_ROPE: return launch_gemm<256, DOTS_EPI_ROPE>(ta, tb, p, st);
         }
     } else {
         p.n_blocks = (N + 127) / 128;
@@ -698,6 +758,20 @@ extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long 
     }
     set_error("dots_gemm_bf16: unknown epilogue %d", epilogue);
     return -1;
+}
+
+extern "C" int dots_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                              int M, int N, int K, int epilogue, const void* bias, const void* residual,
+                              long long ldr, void* stream) {
+    DOTS_REQUIRE(epilogue != DOTS_EPI_ROPE, "dots_gemm_bf16: the rotary epilogue is dots_gemm_bf16_rope");
+    return gemm_bf16_impl(A, lda, W, ldw, out, ldo, M, N, K, epilogue, bias, residual, ldr, nullptr, nullptr, 0, stream);
+}
+
+// ViT q|k|v projection with the 2-D rotary embedding applied to the first rope_cols columns (q heads then k heads, 128 wide) in the
+// GEMM epilogue: out = [rope(bf16(A W_q^T)) | rope(bf16(A W_k^T)) | bf16(A W_v^T)]; cos/sin [M, 64] fp32 (dots_vit_rope_table).
+extern "C" int dots_gemm_bf16_rope(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N, int K,
+                                   const float* cos_t, const float* sin_t, int rope_cols, void* stream) {
+    return gemm_bf16_impl(A, lda, W, ldw, out, ldo, M, N, K, DOTS_EPI_ROPE, nullptr, nullptr, 0, cos_t, sin_t, rope_cols, stream);
 }
 
 // Decode-time (skinny) GEMM, swap-AB + split-K:  partial[s][b][n] = sum_{k in split s} X[b,k] * W[n,k].

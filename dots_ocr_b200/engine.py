@@ -255,14 +255,13 @@ class Engine:
         layers = [x.clone()] if return_layers else None
         for L in self.v_layers:
             ops.rmsnorm(x, L["norm1"], v.rms_norm_eps, out=normed)
-            ops.gemm(normed, L["qkv"], out=qkv)
-            ops.vit_rope_apply(qkv, Hh, cos, sin)
+            ops.gemm_rope(normed, L["qkv"], qkv, cos, sin, 2 * D)          # q|k|v projection + 2-D RoPE of q, k in the epilogue
             ops.attn_varlen(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], attn, cu, max_seqlen, Hh, Hh, False, scale)
             ops.gemm(attn, L["proj"], out=x, epilogue=ops.EPI_RESIDUAL, residual=x)
             ops.rmsnorm(x, L["norm2"], v.rms_norm_eps, out=normed)
             ops.gemm(normed, L["fc13"], out=act, epilogue=ops.EPI_SWIGLU)
             ops.gemm(act, L["fc2"], out=x, epilogue=ops.EPI_RESIDUAL, residual=x)
-            self.launches += 8
+            self.launches += 7
             if return_layers:
                 layers.append(x.clone())
         del qkv, attn, act

@@ -77,6 +77,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, e
     return out
 
 
+def gemm_rope(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, rope_cols: int) -> torch.Tensor:
+    """ViT q|k|v projection with the 2-D rotary embedding of q and k fused into the GEMM epilogue (out [M, N] bf16)."""
+    _bf16_2d(a, "a"); _bf16_2d(w, "w"); _bf16_2d(out, "out")
+    M, Kd = a.shape
+    N = w.shape[0]
+    assert out.shape == (M, N) and cos.dtype == torch.float32 and cos.shape == (M, 64) and sin.shape == (M, 64) and cos.is_contiguous()
+    with _Prof("gemm_bf16_tcgen05", 2.0 * M * N * Kd):
+        rc = _lib.load().dots_gemm_bf16_rope(_p(a), _ll(a.stride(0)), _p(w), _ll(w.stride(0)), _p(out), _ll(out.stride(0)), M, N, Kd,
+                                             _p(cos), _p(sin), int(rope_cols), _stream())
+    _lib.check(rc, "dots_gemm_bf16_rope")
+    return out
+
+
 def gemm_skinny(x: torch.Tensor, w: torch.Tensor, splits: int = 1, partial: Optional[torch.Tensor] = None,
                 out_bf16: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
     """Decode GEMM (batch <= 256).  Returns fp32 partials [splits, B, N] or bf16 [B, N] when out_bf16 is given."""

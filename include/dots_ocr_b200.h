@@ -39,6 +39,7 @@ extern "C" {
 #define DOTS_EPI_F32_PARTIAL_T 5 /* internal: swap-AB split-K partials */
 #define DOTS_EPI_BF16_T 6        /* internal: swap-AB transposed bf16 store */
 #define DOTS_EPI_SWIGLU_T 7      /* internal: swap-AB gate|up GEMM with fused SwiGLU */
+#define DOTS_EPI_ROPE 8          /* internal (dots_gemm_bf16_rope): ViT q|k|v projection + 2-D rotary embedding */
 
 DOTS_API const char* dots_last_error(void);
 DOTS_API int dots_abi_version(void);
@@ -59,6 +60,13 @@ DOTS_API int dots_set_gemm_pair(int enable);
 DOTS_API int dots_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
                    int M, int N, int K, int epilogue, const void* bias, const void* residual, long long ldr,
                    void* stream);
+
+/* ViT q|k|v projection with the 2-D rotary embedding fused into the epilogue ([V]:287 + :295-302): the first rope_cols columns
+ * (q heads then k heads, 128 wide each) are rotated NeoX-style in fp32 after the bf16 rounding of the Linear output -- bit-identical
+ * to dots_gemm_bf16(STORE) followed by dots_vit_rope_apply, without that kernel's read-modify-write pass over q and k.
+ * cos_t / sin_t: [M, 64] fp32 from dots_vit_rope_table. */
+DOTS_API int dots_gemm_bf16_rope(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
+                        int K, const float* cos_t, const float* sin_t, int rope_cols, void* stream);
 
 /* Decode-time skinny GEMM (batch <= 256 rows), swap-AB so the weight matrix is the 128-row tensor-core
  * operand and streams from HBM once.  Either

@@ -482,3 +482,19 @@ def test_gpu_image_processor_equals_host_processor():
         a = eng.encode_images(pv.to(DEV), grid)
         b = eng.encode_pages_u8([img.to(DEV)])
         assert torch.equal(a, b), (H, W)
+
+
+@pytest.mark.parametrize("M,heads", [(43808, 12), (5476, 12), (300, 2), (20000, 12)])
+def test_gemm_rope_epilogue_matches_gemm_then_rope(M, heads, gen):
+    """ViT q|k|v projection with the 2-D rotary embedding in the GEMM epilogue == GEMM + dots_vit_rope_apply, bit for bit (large M runs
+    the CTA-pair kernel with the fused epilogue, small M falls back to the two-kernel path inside the library)."""
+    ops = _ops()
+    D, K = heads * 128, 1536 if heads == 12 else 256
+    a, w = _rand((M, K), gen), _rand((3 * D, K), gen, 0.03)
+    ang = torch.rand((M, 64), generator=gen, device=DEV) * 6.28
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    ref = ops.gemm(a, w)
+    ops.vit_rope_apply(ref, heads, cos, sin)
+    out = torch.full((M, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_rope(a, w, out, cos, sin, 2 * D)
+    assert torch.equal(out, ref)

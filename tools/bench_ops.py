@@ -69,6 +69,30 @@ def main():
                                   pair_tflops=round(2.0 * M * N * K / ms2 / 1e9, 1),
                                   cublas_ms=round(ref, 4), cublas_tflops=round(2.0 * M * N * K / ref / 1e9, 1))), flush=True)
             del a, w
+    if "decode_gemm" in only:
+        # decode GEMMs over pre-tiled operands (bulk copies) vs the tensor-map kernels, weights >> L2 are not possible for one layer, so
+        # each timing loops over 8 distinct weight copies (the step streams a different layer's weights every time)
+        for (B, N, K) in [(64, 2048, 1536), (64, 1536, 1536), (64, 17920, 1536), (64, 1536, 8960), (64, 151936, 1536)]:
+            copies = 1 if N > 100000 else 8
+            ws = [rnd(N, K, scale=0.03) for _ in range(copies)]
+            wts = [ops.tile_weight(w) for w in ws]
+            x = rnd(B, K)
+            xt = ops.tile_rows(x, 64).view(-1)
+            s_ = 1 if N > 10000 else ops.pick_splits(-(-N // 128), -(-K // 64))
+            part = torch.empty((s_, B, N), device=DEV, dtype=torch.float32)
+            it = [0]
+
+            def old():
+                it[0] += 1
+                ops.gemm_skinny(x, ws[it[0] % copies], s_, partial=part)
+
+            def new():
+                it[0] += 1
+                ops.decode_gemm_partial(xt, wts[it[0] % copies], part, B, N, K, s_)
+            for name, fn in (("tensor-map", old), ("bulk-tiled", new)):
+                ms = timeit(fn, iters=16)
+                print(json.dumps(dict(k="decode_gemm", path=name, B=B, N=N, K=K, splits=s_, ms=round(ms, 4), weight_GBs=round(N * K * 2 / ms / 1e6, 1))), flush=True)
+            del ws, wts
     if "skinny" in only:
         for (B, N, K) in [(64, 2048, 1536), (64, 1536, 1536), (64, 17920, 1536), (64, 1536, 8960), (64, 151936, 1536), (1, 17920, 1536)]:
             x, w = rnd(B, K), rnd(N, K, scale=0.03)
@@ -93,6 +117,16 @@ def main():
                     continue
                 print(json.dumps(dict(k="attn", impl=impl, L=L, nseq=nseq, hq=hq, hkv=hkv, causal=causal, ms=round(ms, 4),
                                       tflops=round(fl / ms / 1e9, 1))), flush=True)
+            # the bar: the kernel the reference's HF path really runs (parser.py:68-74 attn_implementation="flash_attention_2";
+            # [V] dots_ocr.py:304-310 flash_attn_varlen_func) -- the in-image flash-attn 2.8 build (library code, mma.sync on sm_100)
+            try:
+                from flash_attn import flash_attn_varlen_func
+                q3, k3, v3 = q.reshape(T, hq, 128), k.reshape(T, hkv, 128), v.reshape(T, hkv, 128)
+                ms = timeit(lambda: flash_attn_varlen_func(q3, k3, v3, cu, cu, L, L, softmax_scale=128 ** -0.5, causal=causal))
+                print(json.dumps(dict(k="attn", impl="flash_attn_2.8_varlen (reference's kernel)", L=L, nseq=nseq, hq=hq, hkv=hkv, causal=causal,
+                                      ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))), flush=True)
+            except Exception as e:      # noqa: BLE001
+                print(json.dumps(dict(k="attn", impl="flash_attn", error=repr(e)[:200])), flush=True)
     if "decode" in only:
         for (B, ctx, splits) in [(64, 1881, 3), (64, 1881, 1), (64, 1881, 6), (1, 1881, 16), (32, 6200, 6)]:
             hq, hkv = 12, 2
