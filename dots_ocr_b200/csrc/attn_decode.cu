@@ -56,6 +56,7 @@ struct DecParams {
     const float* qkv_partial;
     const bf16* qkv_bf16;     // [B][(nq + 2 nkv) * 128], bias already added (dots_decode_gemm_qkv); alternative to qkv_partial
     int qkv_splits;
+    unsigned long long* trace; // timeline instrumentation (nullptr unless armed)
     int out_tile_rows;        // > 0: `out` is written in the k-block-tiled activation layout with this many rows per tile
     int cluster_merge;        // 1: the n_splits CTAs of a (sequence, kv head) are one cluster and merge through DSMEM
     int fault;                // test-only fault injection (dots_debug_set_fault): 1 = key tile 0, 2 = every other key tile loses its P*V term
@@ -124,6 +125,7 @@ attn_decode_kernel(const DecParams p) {
     if (tid == 0) {
         for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], DEC_WARPS); }
         fence_barrier_init();
+        trace_point(p.trace, 20, 0);
     }
     __syncthreads();
 
@@ -146,6 +148,7 @@ attn_decode_kernel(const DecParams p) {
         }
         __syncwarp();
         pdl_wait();
+        if (lane == 0) trace_point(p.trace, 20, 1);
         if (fused && holds_new) {
             // the appended k/v row is produced by the consumer warps of this CTA: wait until they published it
             asm volatile("bar.sync 2, %0;" ::"n"(DEC_THREADS) : "memory");
@@ -265,9 +268,11 @@ attn_decode_kernel(const DecParams p) {
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
 
+    if (tid == 0) trace_point(p.trace, 20, 5);          // prologue (QKV finalize, Q fragments) done
     for (int i = 0; i < n_tiles; ++i) {
         const int stg = i % DEC_STAGES;
         mbar_wait(&full_bar[stg], (i / DEC_STAGES) & 1);
+        if (i == 0 && tid == 0) trace_point(p.trace, 20, 2);
         const int key0 = k_begin + i * DEC_RING_KEYS + warp * DEC_TILE;       // this warp's 16 keys of the tile
         if (key0 >= k_end) {                                                   // warp-uniform: nothing of this slice is visible
             __syncwarp();
@@ -349,6 +354,7 @@ attn_decode_kernel(const DecParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stg]);           // this warp is done with its slice of the stage
     }
+    if (tid == 0) trace_point(p.trace, 20, 3);
     l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 1);
     l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 2);
 
@@ -443,6 +449,7 @@ attn_decode_kernel(const DecParams p) {
             if (c == 0) { p.part_ml[pi * 2] = mv[r]; p.part_ml[pi * 2 + 1] = lv[r]; }
         }
     }
+    if (tid == 0) trace_point(p.trace, 20, 4);
 }
 
 __global__ void __launch_bounds__(DEC_D)
@@ -484,6 +491,7 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
                  DEC_MAX_CLUSTER);
     p.cluster_merge = cluster ? 1 : 0;
     p.fault = g_debug_fault;
+    p.trace = g_trace;
     p.n_q_heads = n_q_heads; p.n_kv_heads = n_kv_heads; p.group = n_q_heads / n_kv_heads; p.n_splits = n_splits;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -8,6 +8,7 @@ namespace dots {
 
 static thread_local char g_err[1024] = "";
 int g_pdl = 1;
+unsigned long long* g_trace = nullptr;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -107,6 +108,11 @@ extern "C" int dots_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (sm_count) *sm_count = prop.multiProcessorCount;
     if (cc_major) *cc_major = prop.major;
     if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+extern "C" int dots_debug_set_trace(void* device_buffer) {
+    dots::g_trace = reinterpret_cast<unsigned long long*>(device_buffer);
     return 0;
 }
 

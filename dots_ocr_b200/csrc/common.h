@@ -47,6 +47,9 @@ bool first_use_on_device(bool (&flags)[64]);
 // predecessor is still running; they call pdl_wait() (ptx.cuh) before touching anything a predecessor writes.
 // dots_set_pdl(0) turns the attribute off globally (plain stream serialisation).
 extern int g_pdl;
+// Timeline instrumentation (dots_debug_set_trace): when non-null, the decode kernels append (kernel id | point | CTA, %globaltimer,
+// clock64) records to this device buffer: word 0 is the record counter, word 1 the capacity in records.  nullptr in normal operation.
+extern unsigned long long* g_trace;
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg{};

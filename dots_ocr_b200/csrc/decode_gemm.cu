@@ -49,6 +49,7 @@ struct DgParams {
     float* stats;            // RESNORM: [n_tiles][64] sums of squares
     unsigned* counter;       // RESNORM: CTAs of this launch that have published their statistics
     float eps;
+    unsigned long long* trace;   // timeline instrumentation (nullptr unless armed)
 };
 
 template <int BN, int CS>
@@ -107,6 +108,8 @@ decode_gemm_cluster_kernel(const DgParams p) {
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     pdl_launch_dependents();
+    constexpr int TRACE_KID = 40 + MODE;
+    if (threadIdx.x == 0) trace_point(p.trace, TRACE_KID, 0);
 
     float acc[BN];          // epilogue warps: this thread's feature row, all batch columns (partial over this CTA's K slice)
     if (warp == 0) {
@@ -121,6 +124,7 @@ decode_gemm_cluster_kernel(const DgParams p) {
                 bulk_load(smem_a + i * S::A_BYTES, wsrc + (size_t)i * S::A_BYTES, S::A_BYTES, &full_bar[i]);
             }
             pdl_wait();
+            trace_point(p.trace, TRACE_KID, 1);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nk; ++i) {
@@ -162,6 +166,7 @@ decode_gemm_cluster_kernel(const DgParams p) {
         if (nk > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
+            if (threadIdx.x == 128) trace_point(p.trace, TRACE_KID, 3);
             const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
@@ -187,6 +192,7 @@ decode_gemm_cluster_kernel(const DgParams p) {
     tc_fence_before();
     __syncwarp();
     cluster_sync_all();             // every partial of this CTA's batch columns has landed in `recv`
+    if (threadIdx.x == 128) trace_point(p.trace, TRACE_KID, 5);
 
     if (warp >= 4) {
         // ===================== epilogue, part 2: fixed-order reduction + fused elementwise stage =====================
@@ -265,6 +271,7 @@ decode_gemm_cluster_kernel(const DgParams p) {
         }
     }
 
+    if (threadIdx.x == 128) trace_point(p.trace, TRACE_KID, 4);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -281,7 +288,9 @@ static int launch_decode_gemm(const DgParams& p, int n_tiles, cudaStream_t st) {
     if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     }
-    DOTS_CHECK_CUDA(launch_ex_cluster(kern, dim3(CS, n_tiles), dim3(DG_THREADS), (size_t)S::TOTAL, st, true, (unsigned)CS, p));
+    DgParams pt = p;
+    pt.trace = g_trace;
+    DOTS_CHECK_CUDA(launch_ex_cluster(kern, dim3(CS, n_tiles), dim3(DG_THREADS), (size_t)S::TOTAL, st, true, (unsigned)CS, pt));
     return 0;
 }
 

@@ -531,9 +531,12 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
 // [splits] strided reads of 32 B per thread, all independent, so the whole reduction is one round of loads.
 __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const float* __restrict__ partial, int splits,
                                                                       bf16* __restrict__ resid, const bf16* __restrict__ w,
-                                                                      bf16* __restrict__ normed, int B, int H, float eps, int tile_rows) {
+                                                                      bf16* __restrict__ normed, int B, int H, float eps, int tile_rows,
+                                                                      unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_point(trace, 30, 0);
     pdl_wait();
     pdl_launch_dependents();
+    if (threadIdx.x == 0) trace_point(trace, 30, 1);
     __shared__ float s_part[8];
     const int b = blockIdx.x;
     const int c = threadIdx.x;
@@ -568,6 +571,7 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
         bf16* dst = tile_rows > 0 ? normed + tiled_row_off(b, c * 8, tile_rows) : normed + (long long)b * H + c * 8;
         *reinterpret_cast<uint4*>(dst) = pack8(f);
     }
+    if (threadIdx.x == 0) trace_point(trace, 30, 4);
 }
 
 // q,k,v = bf16(sum partial + bias); RoPE(q, k) at pos[b]; q -> q_out, k,v -> cache[b, :, pos[b]]
@@ -780,7 +784,7 @@ extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, vo
     DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
     DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && H % 64 == 0), "dots_decode_residual_rmsnorm: bad tile_rows %d", tile_rows);
     const int threads = ((H / 8) + 31) / 32 * 32;
-    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps, tile_rows));
+    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps, tile_rows, g_trace));
     return 0;
 }
 

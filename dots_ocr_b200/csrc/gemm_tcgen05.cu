@@ -39,6 +39,7 @@ struct GemmParams {
     const float* rope_cos;         // [M, 64] fp32
     const float* rope_sin;
     int rope_cols;
+    unsigned long long* trace;     // timeline instrumentation (nullptr unless armed)
 };
 
 constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
@@ -361,6 +362,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);      // warp-uniform for the compiler
     pdl_launch_dependents();        // the next kernel of the stream may begin its own prologue / weight prefetch
+    constexpr int TRACE_KID = 100 + EPI;
+    if (threadIdx.x == 0) trace_point(p.trace, TRACE_KID, 0);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -391,6 +394,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
             pdl_wait();
+            trace_point(p.trace, TRACE_KID, 1);
             int issued = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk, split;
@@ -436,6 +440,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (leader && kb == kb0 && t == (int)blockIdx.x) trace_point(p.trace, TRACE_KID, 2);
                     const uint64_t da = da0 + (uint64_t)(stage * (S::A_BYTES >> 4));
                     const uint64_t db = db0 + (uint64_t)(stage * (S::B_BYTES >> 4));
                     const uint32_t first = (kb > kb0) ? 1u : 0u;
@@ -453,6 +458,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
+            if (leader) trace_point(p.trace, TRACE_KID, 3);
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -476,6 +482,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (threadIdx.x == 128) trace_point(p.trace, TRACE_KID, 4);
     }
 
     tc_fence_before();
@@ -499,7 +506,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     const int tiles = p.m_blocks * p.n_blocks * p.splits;
     const int slots = num_sms() * S::MIN_CTAS;
     const int grid = tiles < slots ? tiles : slots;
-    DOTS_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)S::TOTAL, stream, true, ta, tb, p));
+    GemmParams pt = p;
+    pt.trace = g_trace;
+    DOTS_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)S::TOTAL, stream, true, ta, tb, pt));
     return 0;
 }
 

@@ -272,6 +272,21 @@ __device__ __forceinline__ uint64_t fmul_f32x2(uint64_t a, uint64_t b) {
     return d;
 }
 
+// ---------------------------------------------------------------- timeline instrumentation (tools/decode_timeline.py)
+// One record = 3 x u64: (kernel id << 48 | point << 40 | linear CTA index), %globaltimer [ns], clock64.  `buf` is nullptr unless
+// dots_debug_set_trace() armed it: the cost in normal operation is one predictable branch per call site.
+__device__ __forceinline__ void trace_point(unsigned long long* buf, int kid, int point) {
+    if (buf == nullptr) return;
+    const unsigned long long i = atomicAdd(buf, 1ull);
+    if (i >= buf[1]) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+    buf[2 + 3 * i] = ((unsigned long long)kid << 48) | ((unsigned long long)point << 40) | cta;
+    buf[3 + 3 * i] = t;
+    buf[4 + 3 * i] = (unsigned long long)clock64();
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -485,6 +485,13 @@ def set_decode_cluster(enable: bool) -> None:
     _lib.check(_lib.load().dots_set_decode_cluster(int(bool(enable))), "dots_set_decode_cluster")
 
 
+def debug_set_trace(buf: Optional[torch.Tensor]) -> None:
+    """Arm (int64 CUDA tensor: [0] = 0, [1] = capacity in records, 3 words per record after that) or disarm (None) the kernel timeline."""
+    if buf is not None:
+        assert buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous()
+    _lib.check(_lib.load().dots_debug_set_trace(_p(buf)), "dots_debug_set_trace")
+
+
 def debug_set_fault(code: int) -> None:
     """Test-only fault injection (0 = off); see dots_debug_set_fault."""
     _lib.check(_lib.load().dots_debug_set_fault(int(code)), "dots_debug_set_fault")

@@ -140,6 +140,10 @@ DOTS_API int dots_set_decode_cluster(int enable);
  * attention kernel drops the P*V contribution of the first 64-key tile of every sequence; 2 = of every other key tile. */
 DOTS_API int dots_debug_set_fault(int code);
 
+/* DIAGNOSTIC: arm (device buffer of u64: [0] = record counter, set to 0; [1] = capacity in records; then 3 words per record) or disarm
+ * (NULL) the timeline instrumentation of the decode kernels (tools/decode_timeline.py). */
+DOTS_API int dots_debug_set_trace(void* device_buffer);
+
 /* ---- HBM-bound elementwise / reduction kernels ------------------------------------------------ */
 
 /* pixel_values [rows, cols] fp32 (or bf16) -> bf16 [rows, ldo] zero-padded ([V]:586 `.to(dtype)`). */
