@@ -16,9 +16,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dots_ocr_b200 import config, weights, ops  # noqa: E402
 from dots_ocr_b200.engine import Engine  # noqa: E402
 
-KID = {20: "attn_decode", 30: "residual_rmsnorm", 40: "cluster_gemm_qkv", 41: "cluster_gemm_resnorm", 105: "gemm_partial(F32_T)",
+KID = {115: "gemm_partial+finalize", 20: "attn_decode", 30: "residual_rmsnorm", 40: "cluster_gemm_qkv", 41: "cluster_gemm_resnorm", 105: "gemm_partial(F32_T)",
        106: "gemm_head(BF16_T)", 107: "gemm_swiglu(SWIGLU_T)"}
-POINT = {0: "start", 1: "dep_released", 5: "prologue_done", 2: "first_stage", 3: "last_consumed", 4: "end"}
+POINT = {0: "start", 1: "dep_released", 5: "prologue_done", 2: "first_stage", 3: "last_consumed", 4: "end", 6: "rendezvous_passed", 7: "finalize_done"}
 
 
 def main():
@@ -87,14 +87,15 @@ def main():
         f = lambda p, fn: (fn(pts[p]) - t0) / 1e3 if p in pts else None
         rows.append(dict(kernel=KID.get(L["kid"], str(L["kid"])), ctas=len(L["seen0"]), start=f(0, min), start_last=f(0, max), dep_released=f(1, min),
                          dep_released_last=f(1, max), prologue_done=f(5, max), first_stage=f(2, min), first_stage_last=f(2, max),
-                         last_consumed=f(3, max), end=f(4, max)))
+                         last_consumed=f(3, max), end=max(x for x in (f(4, max), f(7, max)) if x is not None) if (4 in pts or 7 in pts) else None,
+                         rendezvous=f(6, max)))
     step_us = max(r["end"] for r in rows if r["end"] is not None)
     per_layer = [r for r in rows]
     print(json.dumps({"mode": a.mode, "graph": a.graph, "records": n, "kernels_traced": len(rows), "traced_span_us": round(step_us, 1)}))
     # print a window of kernels from the middle of the step
-    kpl = 5 if a.mode == "fused" else 7
+    kpl = 5 if a.mode in ("fused", "tiled") else 7
     lo = 2 * kpl
-    hdr = ["kernel", "ctas", "start", "start_last", "dep_released", "dep_released_last", "prologue_done", "first_stage", "first_stage_last", "last_consumed", "end"]
+    hdr = ["kernel", "ctas", "start", "start_last", "dep_released", "dep_released_last", "prologue_done", "first_stage", "first_stage_last", "last_consumed", "rendezvous", "end"]
     print(" | ".join(hdr))
     base = rows[lo]["start"] if len(rows) > lo else 0.0
     for r in rows[lo: lo + a.show * kpl + 1]:
