@@ -375,7 +375,7 @@ def run_gpu(args):
         roof = {"kernel": ("decode step = one CUDA-graph launch: " + ("cluster split-K tcgen05 GEMMs (reduction, residual, RMSNorm on chip) + "
                            "cluster-merged KV attention + gate|up SwiGLU GEMM + lm_head + argmax" if eng._decode_plan(B)["mode"] == "fused" else
                            "skinny swap-AB tcgen05 GEMMs (split-K) + KV attention + finalize kernels" +
-                           (", operands pre-tiled in HBM and bulk-copied" if eng._decode_plan(B)["mode"] in ("tiled", "tiled7") else ""))),
+                           (", operands pre-tiled in HBM and bulk-copied" if eng._decode_plan(B)["mode"] == "tiled" else ""))),
                 "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
                 "peak_source": peaks["source"] + " (copy bandwidth)",
                 "launch": "one decode step (graph replay)", "algorithmic_bytes_per_launch": round(by / max(1, steps_dec)),
@@ -457,7 +457,7 @@ def main():
     ap.add_argument("--gemm-pair", dest="gemm_pair", type=int, default=None, choices=[0, 1],
                     help="CTA-pair (cta_group::2) kernel for the large prefill GEMMs (default: the library default)")
     ap.add_argument("--no-pdl", dest="no_pdl", action="store_true", help="plain stream order between kernels (A/B runs)")
-    ap.add_argument("--decode-mode", dest="decode_mode", default=None, choices=["tiled", "tiled7", "fused", "perop"],
+    ap.add_argument("--decode-mode", dest="decode_mode", default=None, choices=["tiled", "fused", "perop"],
                     help="decode layer variant (default: the engine default); see Engine.decode_mode")
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="force the key-split count of the decode attention")
     ap.add_argument("--attn-impl", dest="attn_impl", default=None, choices=["tc", "mma"])

@@ -40,15 +40,6 @@ struct GemmParams {
     const float* rope_sin;
     int rope_cols;
     unsigned long long* trace;     // timeline instrumentation (nullptr unless armed)
-    // F32_PARTIAL_T with the split-K "finalize" fused behind a device-wide rendezvous (dots_decode_gemm_partial_resnorm): once every
-    // CTA of the launch has published its partial tiles, CTA b < batch turns row b into  x = bf16(bf16(sum partials) + resid);
-    // resid = x;  normed = bf16(bf16(x * rsqrt(mean x^2 + eps)) * ln_w)  -- the arithmetic of decode_residual_rmsnorm_kernel.
-    bf16* fin_resid;               // [batch, M] row-major, in/out; nullptr: plain partial output
-    const bf16* fin_ln_w;
-    bf16* fin_normed;
-    unsigned* fin_counter;         // zero when the kernel starts
-    float fin_eps;
-    int fin_tile_rows;             // > 0: normed is written k-block-tiled
 };
 
 constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
@@ -371,7 +362,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);      // warp-uniform for the compiler
     pdl_launch_dependents();        // the next kernel of the stream may begin its own prologue / weight prefetch
-    const int TRACE_KID = 100 + EPI + (p.fin_resid != nullptr ? 10 : 0);
+    constexpr int TRACE_KID = 100 + EPI;
     if (threadIdx.x == 0) trace_point(p.trace, TRACE_KID, 0);
 
     if (warp == 0) {
@@ -492,86 +483,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
         if (threadIdx.x == 128) trace_point(p.trace, TRACE_KID, 4);
-        if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
-            if (p.fin_resid != nullptr) {
-                // ---- fused finalize: publish, rendezvous, then CTA b reduces row b (256 epilogue threads, 8 columns each) ----
-                __threadfence();
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                const int et = threadIdx.x - 128;
-                if (et == 0) atomicAdd(p.fin_counter, 1u);
-                const int batch = p.N, H = p.M;
-                if ((int)blockIdx.x < batch) {
-                    if (et == 0) {
-                        const long long t0 = clock64();
-                        while (*reinterpret_cast<volatile unsigned*>(p.fin_counter) < gridDim.x) {
-                            if (clock64() - t0 > 4000000000LL) {
-                                printf("dots: gemm finalize rendezvous watchdog (block %d)\n", (int)blockIdx.x);
-                                __trap();
-                            }
-                        }
-                        __threadfence();
-                    }
-                    asm volatile("bar.sync 3, 256;" ::: "memory");
-                    if (et == 0) trace_point(p.trace, TRACE_KID, 6);
-                    float* s_part = reinterpret_cast<float*>(tmem_ptr + 4);            // 8 floats inside the barrier block
-                    const float* partial = reinterpret_cast<const float*>(p.out);
-                    const long long sstride = (long long)batch * H;
-                    const int nchunks = H >> 3;
-                    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-                        const bool live = et < nchunks;
-                        float x[8];
-                        float ss = 0.f;
-                        if (live) {
-                            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            const float* p0 = partial + (long long)b * H + et * 8;
-                            for (int s0 = 0; s0 < p.splits; s0 += 16) {                  // every load in flight before the first add; adds in split order
-                                float4 a[16], d[16];
-#pragma unroll
-                                for (int u = 0; u < 16; ++u)
-                                    if (s0 + u < p.splits) {
-                                        const float4* ps = reinterpret_cast<const float4*>(p0 + (s0 + u) * sstride);
-                                        a[u] = __ldcg(ps); d[u] = __ldcg(ps + 1);         // L2: the partials were written by other SMs during this kernel
-                                    }
-#pragma unroll
-                                for (int u = 0; u < 16; ++u)
-                                    if (s0 + u < p.splits) {
-                                        acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
-                                        acc[4] += d[u].x; acc[5] += d[u].y; acc[6] += d[u].z; acc[7] += d[u].w;
-                                    }
-                            }
-                            const uint4 rv = reinterpret_cast<const uint4*>(p.fin_resid + (long long)b * H)[et];
-                            const float rr[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y), bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                x[j] = bf16_round(bf16_round(acc[j]) + rr[j]);
-                                ss += x[j] * x[j];
-                            }
-                            reinterpret_cast<uint4*>(p.fin_resid + (long long)b * H)[et] =
-                                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                        if (lane == 0) s_part[warp - 4] = ss;
-                        asm volatile("bar.sync 3, 256;" ::: "memory");
-                        float tot = 0.f;
-                        const int nw = (nchunks + 31) >> 5;                               // same summation order as decode_residual_rmsnorm_kernel
-                        for (int i = 0; i < nw; ++i) tot += s_part[i];
-                        const float r = rsqrtf(tot / (float)H + p.fin_eps);
-                        if (live) {
-                            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.fin_ln_w) + et);
-                            const float g[8] = {bf16_lo(gv.x), bf16_hi(gv.x), bf16_lo(gv.y), bf16_hi(gv.y), bf16_lo(gv.z), bf16_hi(gv.z), bf16_lo(gv.w), bf16_hi(gv.w)};
-                            float f[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = bf16_round(x[j] * r) * g[j];
-                            bf16* dst = p.fin_tile_rows > 0 ? p.fin_normed + tiled_row_off(b, et * 8, p.fin_tile_rows) : p.fin_normed + (long long)b * H + et * 8;
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                        }
-                        asm volatile("bar.sync 3, 256;" ::: "memory");                    // s_part is reused by the next row
-                    }
-                    if (et == 0) trace_point(p.trace, TRACE_KID, 7);
-                }
-            }
-        }
     }
 
     tc_fence_before();
@@ -1022,40 +933,6 @@ extern "C" int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* p
     p.n_blocks = 1;
     p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
     p.b_tiled = reinterpret_cast<const uint8_t*>(Xt);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUtensorMap ta{}, tb{};
-    return batch <= 32 ? launch_gemm<32, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);
-}
-
-// dots_decode_gemm_partial + dots_decode_residual_rmsnorm in ONE launch (o_proj / down_proj of a decode step): the CTAs publish their
-// split-K partial tiles, rendezvous on `counter` (zero at kernel start; dots_decode_embed_rmsnorm re-arms the step's counters), and
-// CTA b < batch then reduces row b in split order, adds the residual and applies the next RMSNorm -- bit-identical to the two-kernel
-// sequence, one kernel boundary and one launch fewer.  Every CTA of the launch is resident at once (grid <= 2 x SMs).
-extern "C" int dots_decode_gemm_partial_resnorm(const void* Xt, const void* Wt, float* partial, void* resid, const void* ln_w, void* normed,
-                                                unsigned int* counter, int batch, int N, int K, int splits, float eps, int tile_rows,
-                                                void* stream) {
-    DOTS_REQUIRE(Xt && Wt && partial && resid && ln_w && normed && counter && batch > 0 && batch <= 64 && N > 0 && K > 0,
-                 "dots_decode_gemm_partial_resnorm: bad arguments batch=%d N=%d K=%d", batch, N, K);
-    DOTS_REQUIRE(N % 8 == 0 && N <= 2048, "dots_decode_gemm_partial_resnorm: N must be a multiple of 8, <= 2048 (one 8-column chunk per finalize thread)");
-    DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && N % 64 == 0), "dots_decode_gemm_partial_resnorm: bad tile_rows %d", tile_rows);
-    GemmParams p{};
-    p.static_is_b = 0;
-    p.M = N; p.N = batch; p.K = K;
-    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
-    if (splits < 1) splits = 1;
-    if (splits > p.num_k_blocks) splits = p.num_k_blocks;
-    p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
-    p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
-    DOTS_REQUIRE(p.splits == splits, "dots_decode_gemm_partial_resnorm: splits=%d does not tile %d k-blocks (would use %d)", splits, p.num_k_blocks, p.splits);
-    p.out = partial; p.ldo = N;
-    p.m_blocks = (N + BLOCK_M - 1) / BLOCK_M;
-    p.n_blocks = 1;
-    p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
-    p.b_tiled = reinterpret_cast<const uint8_t*>(Xt);
-    p.fin_resid = reinterpret_cast<bf16*>(resid);
-    p.fin_ln_w = reinterpret_cast<const bf16*>(ln_w);
-    p.fin_normed = reinterpret_cast<bf16*>(normed);
-    p.fin_counter = counter; p.fin_eps = eps; p.fin_tile_rows = tile_rows;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta{}, tb{};
     return batch <= 32 ? launch_gemm<32, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);

@@ -171,9 +171,7 @@ class Engine:
         self.launches = 0       # C-ABI kernel launches issued (bench.py reports it)
         self.eos_check_every = 64       # decode steps between looks at the finished flags (only when a stop id is given)
         # Decode layer for batches <= 64:
-        #   "tiled"  5 kernels per layer over pre-tiled operands fetched with bulk copies; o_proj / down_proj reduce their split-K
-        #            partials, add the residual and apply the next RMSNorm themselves behind a device-wide rendezvous
-        #   "tiled7" the same with the two finalize steps as separate kernels (7 per layer)
+        #   "tiled"  7 kernels per layer over pre-tiled operands fetched with bulk copies (split-K partials + finalize kernels)
         #   "fused"  5 kernels per layer: cluster split-K GEMMs with the reduction, residual add and RMSNorm on chip (DSMEM)
         #   "perop"  7 kernels per layer over row-major operands and tensor-map copies; the only mode for batches of 65..256
         self.decode_mode = "tiled"
@@ -328,7 +326,7 @@ class Engine:
             if key not in self._fused_ok:
                 self._fused_ok[key] = ops.decode_gemm_max_clusters(key) >= -(-self.cfg.text.hidden_size // 128)
             return "fused" if self._fused_ok[key] else "tiled"
-        return "tiled7" if self.decode_mode == "tiled7" else "tiled"
+        return "tiled"
 
     def _decode_plan(self, B: int):
         t = self.cfg.text
@@ -378,31 +376,20 @@ class Engine:
                 ops.decode_gemm_resnorm(st["act_t"], L["down_t"], st["resid"], nxt, st["normed_t"], st["stats"][1],
                                         st["counters"][2 * li + 1:2 * li + 2], t.rms_norm_eps, I)
             ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
-        elif pl["mode"] in ("tiled", "tiled7"):
+        elif pl["mode"] == "tiled":
             R = st["tile_rows"]
-            merged = pl["mode"] == "tiled"
-            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps,
-                                     counters=st["counters"] if merged else None, tile_rows=R)
+            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
             for li, L in enumerate(self.t_layers):
                 nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
                 ops.decode_gemm_partial(st["normed_t"], L["qkv_w_t"], st["partial"], B, qkv_n, H, pl["qkv"])
                 ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
                                       st["ctx_len"], st["attn_t"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"],
                                       out_tile_rows=R)
-                if merged:
-                    ops.decode_gemm_partial_resnorm(st["attn_t"], L["o_t"], st["partial"], st["resid"], L["ln2"], st["normed_t"],
-                                                    st["counters"][2 * li:2 * li + 1], nq * hd, pl["o"], t.rms_norm_eps, R)
-                else:
-                    ops.decode_gemm_partial(st["attn_t"], L["o_t"], st["partial"], B, H, nq * hd, pl["o"])
-                    ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
+                ops.decode_gemm_partial(st["attn_t"], L["o_t"], st["partial"], B, H, nq * hd, pl["o"])
+                ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
                 ops.decode_gemm_swiglu(st["normed_t"], L["gu_t"], st["act_t"], B, H)
-                if merged:
-                    # one partial buffer serves both launches: o_proj has completed before down_proj's epilogue stores (dependency wait)
-                    ops.decode_gemm_partial_resnorm(st["act_t"], L["down_t"], st["partial"], st["resid"], nxt, st["normed_t"],
-                                                    st["counters"][2 * li + 1:2 * li + 2], I, pl["down"], t.rms_norm_eps, R)
-                else:
-                    ops.decode_gemm_partial(st["act_t"], L["down_t"], st["partial"], B, H, I, pl["down"])
-                    ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed_t"], t.rms_norm_eps, tile_rows=R)
+                ops.decode_gemm_partial(st["act_t"], L["down_t"], st["partial"], B, H, I, pl["down"])
+                ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed_t"], t.rms_norm_eps, tile_rows=R)
             ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
         else:
             ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
@@ -476,7 +463,7 @@ class Engine:
     def launches_per_decode_step(self, B: int) -> int:
         pl = self._decode_plan(B)
         combine = 1 if pl["attn"] > 1 and not (ops.DECODE_CLUSTER and pl["attn"] <= ops.ATTN_DECODE_MAX_CLUSTER) else 0
-        per_layer = (5 if pl["mode"] in ("fused", "tiled") else 7) + combine
+        per_layer = (5 if pl["mode"] == "fused" else 7) + combine
         return 1 + per_layer * len(self.t_layers) + 2
 
     @_on_device

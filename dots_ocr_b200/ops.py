@@ -427,19 +427,6 @@ def decode_gemm_partial(xt: torch.Tensor, wt: torch.Tensor, partial: torch.Tenso
     return partial
 
 
-def decode_gemm_partial_resnorm(xt: torch.Tensor, wt: torch.Tensor, partial: torch.Tensor, resid: torch.Tensor, ln_w: torch.Tensor,
-                                normed: torch.Tensor, counter: torch.Tensor, K: int, splits: int, eps: float, tile_rows: int) -> None:
-    """o_proj / down_proj of a decode step: split-K partials + (after a device-wide rendezvous) residual add + next RMSNorm, one launch."""
-    _bf16_2d(resid, "resid")
-    B, N = resid.shape
-    assert resid.is_contiguous() and counter.dtype == torch.int32
-    _tiled_act_ok(xt, B, K, "xt"); _tiled_w_ok(wt, N, K, "wt")
-    assert partial.dtype == torch.float32 and partial.numel() >= splits * B * N
-    rc = _lib.load().dots_decode_gemm_partial_resnorm(_p(xt), _p(wt), _p(partial), _p(resid), _p(ln_w), _p(normed), _p(counter), B, N, K, splits,
-                                                      C.c_float(eps), int(tile_rows), _stream())
-    _lib.check(rc, "dots_decode_gemm_partial_resnorm")
-
-
 def decode_gemm_swiglu(xt: torch.Tensor, wt: torch.Tensor, act_t: torch.Tensor, batch: int, K: int) -> torch.Tensor:
     """gate|up + SwiGLU of a decode step over tiled operands; act_t (k-block-tiled [batch, I]) is the B operand of down_proj."""
     two_i = wt.shape[0] * 128

@@ -254,14 +254,6 @@ DOTS_API int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act_t
 /* Split-K partials over tiled operands: partial[s][b][n] fp32 (dots_gemm_skinny_bf16 with bulk-copied operands). */
 DOTS_API int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* partial, int batch, int N, int K, int splits, void* stream);
 
-/* dots_decode_gemm_partial + dots_decode_residual_rmsnorm in one launch (o_proj / down_proj): after a device-wide rendezvous on
- * `counter` (one uint32, zero at kernel start) CTA b reduces row b of the partials in split order, adds the residual and applies the
- * next RMSNorm (bit-identical to the two-kernel sequence).  resid [batch, N] row-major in/out; normed row-major (tile_rows = 0) or
- * k-block-tiled. */
-DOTS_API int dots_decode_gemm_partial_resnorm(const void* Xt, const void* Wt, float* partial, void* resid, const void* ln_w,
-                                     void* normed, unsigned int* counter, int batch, int N, int K, int splits, float eps,
-                                     int tile_rows, void* stream);
-
 /* lm_head of one decode step, batch <= 64: out[b, n] = bf16(X . W^T), row-major.  x_tile_rows = 32 / 64: X is k-block-tiled;
  * x_tile_rows = 0: X is row-major with pitch ldx (first token after prefill). */
 DOTS_API int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_rows, const void* Wt, void* out_bf16, long long ldo,

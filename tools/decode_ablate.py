@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dots_ocr_b200 import config, weights, ops  # noqa: E402
 from dots_ocr_b200.engine import Engine  # noqa: E402
 
-OPS = ("decode_gemm_partial_resnorm", "decode_gemm_partial", "decode_gemm_swiglu", "decode_gemm_head", "gemm_skinny", "gemm_skinny_swiglu", "attn_decode_fused", "attn_decode_qkv", "decode_residual_rmsnorm", "decode_embed_rmsnorm",
+OPS = ("decode_gemm_partial", "decode_gemm_swiglu", "decode_gemm_head", "gemm_skinny", "gemm_skinny_swiglu", "attn_decode_fused", "attn_decode_qkv", "decode_residual_rmsnorm", "decode_embed_rmsnorm",
        "argmax_advance", "decode_gemm_qkv", "decode_gemm_resnorm")
 
 
@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ctx", type=int, default=1881)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--mode", default="tiled", choices=["tiled", "tiled7", "fused", "perop"], help="decode layer variant (Engine.decode_mode)")
+    ap.add_argument("--mode", default="tiled", choices=["tiled", "fused", "perop"], help="decode layer variant (Engine.decode_mode)")
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="override the flash-decoding split count of the plan")
     ap.add_argument("--no-cluster", action="store_true", help="combine kernel instead of the cluster merge for 2..4 attention splits")
     ap.add_argument("--quick", action="store_true", help="only the full step and the attention ablation")
@@ -96,14 +96,6 @@ def main():
                  ("argmax", [("argmax_advance", None)]),
                  ("all gemms", [("decode_gemm_qkv", None), ("decode_gemm_resnorm", None), ("decode_gemm_swiglu", None), ("decode_gemm_head", None)])]
     elif pl["mode"] == "tiled":
-        cases = [("attention(+qkv finalize)", [("attn_decode_fused", None)]),
-                 ("qkv gemm", [("decode_gemm_partial", L0["qkv_w_t"].shape)]),
-                 ("o gemm + finalize", [("decode_gemm_partial_resnorm", L0["o_t"].shape)]),
-                 ("down gemm + finalize", [("decode_gemm_partial_resnorm", L0["down_t"].shape)]), ("lm_head gemm", [("decode_gemm_head", None)]),
-                 ("gate|up gemm + swiglu", [("decode_gemm_swiglu", None)]),
-                 ("argmax", [("argmax_advance", None)]),
-                 ("all gemms", [("decode_gemm_partial", None), ("decode_gemm_partial_resnorm", None), ("decode_gemm_swiglu", None), ("decode_gemm_head", None)])]
-    elif pl["mode"] == "tiled7":
         cases = [("attention(+qkv finalize)", [("attn_decode_fused", None)]),
                  ("qkv gemm", [("decode_gemm_partial", L0["qkv_w_t"].shape)]), ("o gemm", [("decode_gemm_partial", L0["o_t"].shape)]),
                  ("down gemm", [("decode_gemm_partial", L0["down_t"].shape)]), ("lm_head gemm", [("decode_gemm_head", None)]),

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dots_ocr_b200 import config, weights, ops  # noqa: E402
 from dots_ocr_b200.engine import Engine  # noqa: E402
 
-KID = {115: "gemm_partial+finalize", 20: "attn_decode", 30: "residual_rmsnorm", 40: "cluster_gemm_qkv", 41: "cluster_gemm_resnorm", 105: "gemm_partial(F32_T)",
+KID = {20: "attn_decode", 30: "residual_rmsnorm", 40: "cluster_gemm_qkv", 41: "cluster_gemm_resnorm", 105: "gemm_partial(F32_T)",
        106: "gemm_head(BF16_T)", 107: "gemm_swiglu(SWIGLU_T)"}
 POINT = {0: "start", 1: "dep_released", 5: "prologue_done", 2: "first_stage", 3: "last_consumed", 4: "end", 6: "rendezvous_passed", 7: "finalize_done"}
 
@@ -93,7 +93,7 @@ def main():
     per_layer = [r for r in rows]
     print(json.dumps({"mode": a.mode, "graph": a.graph, "records": n, "kernels_traced": len(rows), "traced_span_us": round(step_us, 1)}))
     # print a window of kernels from the middle of the step
-    kpl = 5 if a.mode in ("fused", "tiled") else 7
+    kpl = 5 if a.mode == "fused" else 7
     lo = 2 * kpl
     hdr = ["kernel", "ctas", "start", "start_last", "dep_released", "dep_released_last", "prologue_done", "first_stage", "first_stage_last", "last_consumed", "rendezvous", "end"]
     print(" | ".join(hdr))
