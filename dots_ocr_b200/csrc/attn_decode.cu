@@ -262,16 +262,38 @@ attn_decode_kernel(const DecParams p) {
         for (int kk = 0; kk < 8; ++kk) ldmatrix_x4(qf[kk], smem_u32(sQ) + swz128(r, kk * 2 + (lane >> 4)));
     }
 
+    // Only rows 0..7 of the 16-row MMA tile carry q heads (group <= 8); rows 8..15 are zero padding, so the softmax works on the
+    // first row half of every fragment and feeds P = 0 for the second (their accumulators o[.][2..3] stay 0).  The kernel is bound
+    // by the instruction stream of its four consumer warps (ncu: 20 % issue utilisation with one warp per scheduler, ~4 cycles per
+    // dependent instruction), so the loop is kept lean: per-lane ldmatrix offsets hoisted, no masking arithmetic on full tiles,
+    // the O rescale skipped while the running maximum does not move, no clock reads in the barrier wait.
     float o[16][4];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
+    uint32_t off_k[8], off_v[8];
+    {
+        const int r_k = warp * DEC_TILE + (lane & 7) + 8 * (lane >> 4);
+        const int r_v = warp * DEC_TILE + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            off_k[kk] = dec_tile_off(r_k, kk * 2 + ((lane >> 3) & 1));
+            off_v[kk] = 2 * DEC_BOX_BYTES + dec_tile_off(r_v, kk * 2 + (lane >> 4));
+        }
+    }
+    const uint32_t ring_u32 = smem_u32(ring);
+    const float sc = p.scale_log2;
 
     if (tid == 0) trace_point(p.trace, 20, 5);          // prologue (QKV finalize, Q fragments) done
     for (int i = 0; i < n_tiles; ++i) {
         const int stg = i % DEC_STAGES;
-        mbar_wait(&full_bar[stg], (i / DEC_STAGES) & 1);
+        {
+            uint32_t spins = 0;
+            while (!mbar_try_wait(&full_bar[stg], (i / DEC_STAGES) & 1)) {
+                if (++spins > (1u << 27)) { printf("dots: attn_decode mbarrier watchdog block %d\n", (int)blockIdx.z); __trap(); }
+            }
+        }
         if (i == 0 && tid == 0) trace_point(p.trace, 20, 2);
         const int key0 = k_begin + i * DEC_RING_KEYS + warp * DEC_TILE;       // this warp's 16 keys of the tile
         if (key0 >= k_end) {                                                   // warp-uniform: nothing of this slice is visible
@@ -279,9 +301,9 @@ attn_decode_kernel(const DecParams p) {
             if (lane == 0) mbar_arrive(&empty_bar[stg]);
             continue;
         }
-        const uint32_t kb = smem_u32(ring + stg * DEC_STAGE_BYTES);
-        const uint32_t vb = kb + 2 * DEC_BOX_BYTES;
-        if (key0 + DEC_TILE > k_end) {
+        const uint32_t sb = ring_u32 + stg * DEC_STAGE_BYTES;
+        const bool ragged = key0 + DEC_TILE > k_end;                           // warp-uniform: only the last tile of a sequence
+        if (ragged) {
             // rows past the last visible key hold whatever the cache stripe contains (possibly NaN bit patterns): zero the V
             // rows so that P = 0 really contributes 0 (K rows are neutralised by the -inf select below)
             for (int idx = lane; idx < DEC_TILE * 16; idx += 32) {
@@ -289,7 +311,7 @@ attn_decode_kernel(const DecParams p) {
                 if (key0 + r >= k_end)
                     *reinterpret_cast<uint4*>(ring + stg * DEC_STAGE_BYTES + 2 * DEC_BOX_BYTES + dec_tile_off(warp * DEC_TILE + r, c)) = make_uint4(0, 0, 0, 0);
             }
-            fence_proxy_async_smem();       // these generic-proxy writes precede any later TMA refill of the stage
+            fence_proxy_async_smem();       // these generic-proxy writes precede any later bulk refill of the stage
             __syncwarp();
         }
 
@@ -297,57 +319,40 @@ attn_decode_kernel(const DecParams p) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             uint32_t bfr[4];
-            const int r = warp * DEC_TILE + (lane & 7) + 8 * (lane >> 4);
-            ldmatrix_x4(bfr, kb + dec_tile_off(r, kk * 2 + ((lane >> 3) & 1)));
+            ldmatrix_x4(bfr, sb + off_k[kk]);
             mma_bf16_16816(s[0], qf[kk], bfr[0], bfr[1]);
             mma_bf16_16816(s[1], qf[kk], bfr[2], bfr[3]);
         }
-        float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float val = s[nb][e] * p.scale_log2;
-                const int kj = key0 + nb * 8 + 2 * t + (e & 1);
-                if (kj >= k_end) val = -INFINITY;
-                s[nb][e] = val;
-                mx[e >> 1] = fmaxf(mx[e >> 1], val);
-            }
+        // row g of the tile: keys 2t, 2t+1 (s[0][0..1]) and 8+2t, 8+2t+1 (s[1][0..1])
+        float v0 = s[0][0] * sc, v1 = s[0][1] * sc, v2 = s[1][0] * sc, v3 = s[1][1] * sc;
+        if (ragged) {
+            const int kj = key0 + 2 * t;
+            if (kj >= k_end) v0 = -INFINITY;
+            if (kj + 1 >= k_end) v1 = -INFINITY;
+            if (kj + 8 >= k_end) v2 = -INFINITY;
+            if (kj + 9 >= k_end) v3 = -INFINITY;
         }
-        float alpha[2], msafe[2];
+        float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run[0], mx);
+        const float msafe = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = fast_exp2(m_run[0] - msafe);
+        m_run[0] = m_new;
+        const float p0 = fast_exp2(v0 - msafe), p1 = fast_exp2(v1 - msafe), p2 = fast_exp2(v2 - msafe), p3 = fast_exp2(v3 - msafe);
+        l_run[0] *= alpha;
+        l_run[0] += p0 + p1;
+        l_run[0] += p2 + p3;
+        uint32_t pf[4] = {pack_bf16x2(p0, p1), 0u, pack_bf16x2(p2, p3), 0u};
+        if ((p.fault == 1 && i == 0 && split == 0) || (p.fault == 2 && (i & 1) == 0)) pf[0] = pf[2] = 0u;   // test-only fault
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {          // the running maximum moved for some row of this warp: rescale O
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-            const float m_new = fmaxf(m_run[h], mx[h]);
-            msafe[h] = (m_new == -INFINITY) ? 0.f : m_new;
-            alpha[h] = fast_exp2(m_run[h] - msafe[h]);
-            m_run[h] = m_new;
-            l_run[h] *= alpha[h];
-        }
-        uint32_t pf[4];
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-            const float p0 = fast_exp2(s[nb][0] - msafe[0]);
-            const float p1 = fast_exp2(s[nb][1] - msafe[0]);
-            const float p2 = fast_exp2(s[nb][2] - msafe[1]);
-            const float p3 = fast_exp2(s[nb][3] - msafe[1]);
-            l_run[0] += p0 + p1;
-            l_run[1] += p2 + p3;
-            pf[nb * 2 + 0] = pack_bf16x2(p0, p1);
-            pf[nb * 2 + 1] = pack_bf16x2(p2, p3);
-        }
-        if ((p.fault == 1 && i == 0 && split == 0) || (p.fault == 2 && (i & 1) == 0)) pf[0] = pf[1] = pf[2] = pf[3] = 0u;   // test-only fault
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
-            o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
+            for (int j = 0; j < 16; ++j) { o[j][0] *= alpha; o[j][1] *= alpha; }
         }
 #pragma unroll
         for (int dp = 0; dp < 8; ++dp) {
             uint32_t bfr[4];
-            const int r = warp * DEC_TILE + (lane & 7) + 8 * ((lane >> 3) & 1);
-            ldmatrix_x4_trans(bfr, vb + dec_tile_off(r, dp * 2 + (lane >> 4)));
+            ldmatrix_x4_trans(bfr, sb + off_v[dp]);
             mma_bf16_16816(o[2 * dp], pf, bfr[0], bfr[1]);
             mma_bf16_16816(o[2 * dp + 1], pf, bfr[2], bfr[3]);
         }
