@@ -112,6 +112,48 @@ __global__ void stream2d_kernel(const __grid_constant__ CUtensorMap tm, int boxe
     }
 }
 
+// ------------------------------------------------------------------------------------------------ KV-attention access pattern
+// The decode attention kernel's traffic without its arithmetic: CTA i streams the K stripe and the V stripe of one (sequence, kv
+// head) -- two sequential streams `stride` bytes apart from its neighbours', 16 KB per tile each -- through a ring whose stage holds
+// one K tile + one V tile; a consumer warp waits `spin` clocks per stage before releasing it (0 = memory system only).
+__global__ void kv_stream_kernel(const uint8_t* __restrict__ kbase, const uint8_t* __restrict__ vbase, size_t stride, int tiles, int stages,
+                                 int spin, unsigned* sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 32;
+    uint8_t* ring = smem + 1024;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t* ks = kbase + (size_t)blockIdx.x * stride;
+    const uint8_t* vs = vbase + (size_t)blockIdx.x * stride;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < tiles; ++i) {
+                const int st = i % stages;
+                if (i >= stages) mbar_wait(&empty[st], ((i / stages) & 1) ^ 1);
+                mbar_expect_tx(&full[st], 32768);
+                bulk_load(ring + (size_t)st * 32768, ks + (size_t)i * 16384, 16384, &full[st]);
+                bulk_load(ring + (size_t)st * 32768 + 16384, vs + (size_t)i * 16384, 16384, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        unsigned acc = 0;
+        for (int i = 0; i < tiles; ++i) {
+            const int st = i % stages;
+            mbar_wait(&full[st], (i / stages) & 1);
+            acc += *reinterpret_cast<const volatile unsigned*>(ring + (size_t)st * 32768 + lane * 4);
+            if (spin > 0) { const long long t0 = clock64(); while (clock64() - t0 < spin) {} }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        if (acc == 0x12345678u) sink[0] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pdl chain
 // Kernel i: wait for kernel i-1, read what it wrote (148 x 128 floats), add 1, write.  A real producer/consumer boundary.
 __global__ void chain_kernel(const float* __restrict__ in, float* __restrict__ out, int use_pdl) {
@@ -247,6 +289,37 @@ int main(int argc, char** argv) {
         }
         CK(cudaFree(src)); CK(cudaFree(sink));
     }
+
+    // ---- decode-attention access pattern: 128 (and 148, 256) CTAs x (K stripe + V stripe), 30 tiles of 16 KB each per stripe
+    {
+        const size_t stride = (size_t)2240 * 256;                 // one (sequence, kv head) stripe: ctx_max 2240 keys x 256 B
+        const size_t layer = stride * 256;                        // room for up to 256 stripes
+        const int L = 24;                                         // distinct "layers" so that nothing is served from L2
+        uint8_t *kb, *vb; CK(cudaMalloc(&kb, layer * L)); CK(cudaMalloc(&vb, layer * L));
+        CK(cudaMemset(kb, 1, layer * L)); CK(cudaMemset(vb, 2, layer * L));
+        unsigned* sink; CK(cudaMalloc(&sink, 4));
+        CK(cudaFuncSetAttribute(kv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        for (int ctas : {128, 148, 256}) {
+            for (int stages : {3, 4, 6}) {
+                for (int spin : {0, 800, 1600}) {
+                    size_t smem = 1024 + (size_t)stages * 32768;
+                    if (ctas > 148 && smem * 2 > 224 * 1024) continue;
+                    kv_stream_kernel<<<ctas, 64, smem, st>>>(kb, vb, stride, 30, stages, spin, sink);
+                    CK(cudaEventRecord(e0, st));
+                    for (int l = 1; l < L; ++l) kv_stream_kernel<<<ctas, 64, smem, st>>>(kb + layer * l, vb + layer * l, stride, 30, stages, spin, sink);
+                    CK(cudaEventRecord(e1, st));
+                    CK(cudaStreamSynchronize(st));
+                    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                    const double bytes = (double)ctas * 30 * 32768 * (L - 1);
+                    printf("{\"k\": \"kv_stream\", \"ctas\": %d, \"stages\": %d, \"consumer_spin_clk\": %d, \"us_per_launch\": %.2f, \"gbs\": %.0f}\n", ctas, stages, spin,
+                           ms * 1e3 / (L - 1), bytes / ms / 1e6);
+                    fflush(stdout);
+                }
+            }
+        }
+        CK(cudaFree(kb)); CK(cudaFree(vb)); CK(cudaFree(sink));
+    }
+    if (argc > 2) return 0;                                       // "quick kv": only the KV pattern
 
     // ---- 2-D tensor-map streaming: [rows, pitch] bf16, boxes of box_rows x 64 elements (128-B rows)
     {
