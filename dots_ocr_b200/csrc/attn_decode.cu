@@ -26,15 +26,26 @@ namespace dots {
 
 constexpr int DEC_D = 128;
 constexpr int DEC_TILE = 16;                 // keys per warp per ring tile
-constexpr int DEC_WARPS = 4;                 // consumer warps
+constexpr int DEC_SLICES = 4;                // 16-key slices of a ring tile, one consumer warp each
+#ifndef DEC_GROUPS_OVR
+#define DEC_GROUPS_OVR 2
+#endif
+// Consumer groups: group g works on ring tiles g, g + GROUPS, ... with its own running (m, l, O).  One tile costs a warp a ~900-cycle
+// DEPENDENT chain (barrier wake -> ldmatrix -> 8 chained HMMAs -> max/shuffles -> exp2 -> 16 HMMAs -> arrive) at 16 % issue
+// utilisation, so with one group the kernel streams at one tile per ~0.9 us per SM (4.6 TB/s) whatever the ring depth; two groups
+// keep two tiles in progress per SM (profiles/microbench_r2.md: the same traffic without arithmetic takes 21 us, 5.9 TB/s).
+constexpr int DEC_GROUPS = DEC_GROUPS_OVR;
+constexpr int DEC_WARPS = DEC_SLICES * DEC_GROUPS;                         // consumer warps
 constexpr int DEC_THREADS = (DEC_WARPS + 1) * 32;                          // + producer warp
-constexpr int DEC_RING_KEYS = DEC_TILE * DEC_WARPS;                        // 64 keys per ring tile
+constexpr int DEC_RING_KEYS = DEC_TILE * DEC_SLICES;                       // 64 keys per ring tile
 constexpr int DEC_BOX_BYTES = DEC_RING_KEYS * 128;                         // [64 keys][64 dims] bf16 = 8 KB (one swizzle box)
 constexpr int DEC_STAGE_BYTES = 4 * DEC_BOX_BYTES;                         // K lo | K hi | V lo | V hi = 32 KB
 #ifndef DEC_STAGES_OVR
-#define DEC_STAGES_OVR 3
+#define DEC_STAGES_OVR 4
 #endif
 constexpr int DEC_STAGES = DEC_STAGES_OVR;
+// a ring stage must always serve the same consumer group (a group that skipped a phase of a barrier could not tell it from the next)
+static_assert(DEC_STAGES % DEC_GROUPS == 0, "ring depth must be a multiple of the number of consumer groups");
 constexpr int DEC_SMEM = 1024 /*align*/ + 4096 /*Q*/ + DEC_STAGES * DEC_STAGE_BYTES + 256 /*barriers*/;
 constexpr int DEC_MAX_CLUSTER = 4;                                         // splits merged on chip
 constexpr int DEC_MERGE_BYTES = 8 * DEC_D * 4 + 8 * 2 * 4;                 // one peer's partial: O [<= 8 heads][128] + (m, l) [<= 8]
@@ -123,7 +134,7 @@ attn_decode_kernel(const DecParams p) {
     const bool holds_new = (ctx - 1 >= k_begin) && (ctx - 1 < k_end);
 
     if (tid == 0) {
-        for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], DEC_WARPS); }
+        for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], DEC_SLICES); }
         fence_barrier_init();
         trace_point(p.trace, 20, 0);
     }
@@ -272,10 +283,11 @@ attn_decode_kernel(const DecParams p) {
     for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
+    const int slice = warp % DEC_SLICES, grp = warp / DEC_SLICES;
     uint32_t off_k[8], off_v[8];
     {
-        const int r_k = warp * DEC_TILE + (lane & 7) + 8 * (lane >> 4);
-        const int r_v = warp * DEC_TILE + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int r_k = slice * DEC_TILE + (lane & 7) + 8 * (lane >> 4);
+        const int r_v = slice * DEC_TILE + (lane & 7) + 8 * ((lane >> 3) & 1);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             off_k[kk] = dec_tile_off(r_k, kk * 2 + ((lane >> 3) & 1));
@@ -286,7 +298,7 @@ attn_decode_kernel(const DecParams p) {
     const float sc = p.scale_log2;
 
     if (tid == 0) trace_point(p.trace, 20, 5);          // prologue (QKV finalize, Q fragments) done
-    for (int i = 0; i < n_tiles; ++i) {
+    for (int i = grp; i < n_tiles; i += DEC_GROUPS) {
         const int stg = i % DEC_STAGES;
         {
             uint32_t spins = 0;
@@ -295,7 +307,7 @@ attn_decode_kernel(const DecParams p) {
             }
         }
         if (i == 0 && tid == 0) trace_point(p.trace, 20, 2);
-        const int key0 = k_begin + i * DEC_RING_KEYS + warp * DEC_TILE;       // this warp's 16 keys of the tile
+        const int key0 = k_begin + i * DEC_RING_KEYS + slice * DEC_TILE;      // this warp's 16 keys of the tile
         if (key0 >= k_end) {                                                   // warp-uniform: nothing of this slice is visible
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stg]);
@@ -309,7 +321,7 @@ attn_decode_kernel(const DecParams p) {
             for (int idx = lane; idx < DEC_TILE * 16; idx += 32) {
                 const int r = idx >> 4, c = idx & 15;
                 if (key0 + r >= k_end)
-                    *reinterpret_cast<uint4*>(ring + stg * DEC_STAGE_BYTES + 2 * DEC_BOX_BYTES + dec_tile_off(warp * DEC_TILE + r, c)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(ring + stg * DEC_STAGE_BYTES + 2 * DEC_BOX_BYTES + dec_tile_off(slice * DEC_TILE + r, c)) = make_uint4(0, 0, 0, 0);
             }
             fence_proxy_async_smem();       // these generic-proxy writes precede any later bulk refill of the stage
             __syncwarp();
@@ -366,7 +378,7 @@ attn_decode_kernel(const DecParams p) {
     // ---- merge the 4 warps (rows g < group only; rows 8..15 are padding) -----------------
     asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");   // all consumer warps done with the ring (every TMA tile has landed)
     float* sO = reinterpret_cast<float*>(ring);                         // [4 warps][8 rows][128]
-    float* sML = sO + DEC_WARPS * 8 * DEC_D;                            // [4 warps][8 rows][2]
+    float* sML = sO + DEC_WARPS * 8 * DEC_D;                            // [warps][8 rows][2]
 #pragma unroll
     for (int nb = 0; nb < 16; ++nb) {
         sO[(warp * 8 + g) * DEC_D + nb * 8 + 2 * t] = o[nb][0];
@@ -377,14 +389,15 @@ attn_decode_kernel(const DecParams p) {
         sML[(warp * 8 + g) * 2 + 1] = l_run[0];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");
-    // thread tid owns head dim c = tid of every q head r of the group (DEC_WARPS * 32 == DEC_D)
-    static_assert(DEC_WARPS * 32 == DEC_D, "one consumer thread per head dim");
+    // the first DEC_D consumer threads finish: thread c owns head dim c of every q head r of the group
+    static_assert(DEC_WARPS * 32 >= DEC_D && DEC_WARPS * 8 * (DEC_D + 2) * 4 <= DEC_STAGES * DEC_STAGE_BYTES, "merge scratch lives in the ring");
     const int c = tid;
+    const bool finisher = tid < DEC_D;
     float accv[8], mv[8], lv[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         accv[r] = 0.f; mv[r] = -INFINITY; lv[r] = 0.f;
-        if (r < p.group) {
+        if (finisher && r < p.group) {
             float m = -INFINITY;
 #pragma unroll
             for (int w = 0; w < DEC_WARPS; ++w) m = fmaxf(m, sML[(w * 8 + r) * 2]);
@@ -402,12 +415,12 @@ attn_decode_kernel(const DecParams p) {
     if (p.n_splits == 1) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (r < p.group)
+            if (finisher && r < p.group)
                 p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
     } else if (p.cluster_merge) {
         // ---- on-chip merge across the cluster: peers write (O, m, l) into the leader's shared memory, the leader combines
         //      in split order (same arithmetic as attn_decode_combine_kernel) ----
-        if (split != 0) {
+        if (split != 0 && finisher) {
             const uint32_t base = mapa_shared(smem_u32(sMerge + (size_t)(split - 1) * DEC_MERGE_BYTES), 0);
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -422,7 +435,7 @@ attn_decode_kernel(const DecParams p) {
             }
         }
         cluster_sync_all();
-        if (split == 0) {
+        if (split == 0 && finisher) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 if (r >= p.group) continue;
@@ -445,7 +458,7 @@ attn_decode_kernel(const DecParams p) {
                 p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
             }
         }
-    } else {
+    } else if (finisher) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             if (r >= p.group) continue;

@@ -341,7 +341,8 @@ class Engine:
         else:
             # one CTA per (sequence, kv head) once that alone covers most SMs; flash-decoding splits below (<= 4 merge inside a
             # cluster, more go through the combine kernel)
-            attn = 1 if pairs >= (3 * self.sms) // 4 else max(1, min(16, (2 * self.sms) // pairs))
+            # (the attention CTA keeps a 128 KB K/V ring: one CTA per SM)
+            attn = 1 if pairs >= (3 * self.sms) // 4 else max(1, min(16, self.sms // pairs))
         return dict(
             mode=mode, fused=(mode == "fused"),
             qkv=ops.pick_splits(tiles(qkv_n), kb(H), self.sms),
