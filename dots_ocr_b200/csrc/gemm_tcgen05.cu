@@ -40,6 +40,7 @@ struct GemmParams {
     const float* rope_sin;
     int rope_cols;
     unsigned long long* trace;     // timeline instrumentation (nullptr unless armed)
+    int stages;                    // ring depth of this launch (0: the template's STAGES)
 };
 
 constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
@@ -53,10 +54,13 @@ struct GemmSmem {
     // Decode (swap-AB) kernels keep the ring under half an SM's shared memory so that two CTAs -- usually of two
     // consecutive kernels of the decode step, overlapped by programmatic dependent launch -- stream weights at once.
 #ifndef GEMM_SWAP_STAGES
-#define GEMM_SWAP_STAGES 4
+#define GEMM_SWAP_STAGES 6
 #endif
     static constexpr int STAGES = SWAP ? (BLOCK_N >= 256 ? 2 : (BLOCK_N >= 128 ? 4 : GEMM_SWAP_STAGES)) : (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-    static constexpr int MIN_CTAS_ = (SWAP && BLOCK_N <= 128 && STAGES * STAGE_BYTES <= 100 * 1024) ? 2 : 1;
+    // STAGES is the maximum ring depth of the decode kernels; a launch picks its own depth (GemmParams::stages, <= STAGES) and asks
+    // for that much shared memory only, so that short kernels (q|k|v: 3 k-blocks per CTA, o_proj: 2) leave room for their neighbours
+    // on the SM and long ones (gate|up: 24) keep more bytes in flight.  Two CTAs per SM by registers for the narrow batch tiles.
+    static constexpr int MIN_CTAS_ = (SWAP && BLOCK_N <= 64) ? 2 : 1;
     static constexpr int MIN_CTAS = MIN_CTAS_;
     static constexpr int BAR_BYTES = 1024;
     // SWIGLU_T: the up-projection warps hand their bf16-rounded values to the gate warps through shared memory
@@ -321,15 +325,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, GemmSmem<BLOCK_N, EPI>::MIN_CTAS
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
     using S = GemmSmem<BLOCK_N, EPI>;
-    constexpr int STAGES = S::STAGES;
+    constexpr int MAX_STAGES = S::STAGES;
+    const int STAGES = (p.stages > 0 && p.stages < MAX_STAGES) ? p.stages : MAX_STAGES;      // ring depth of this launch
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * S::A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-    uint64_t* full_bar = bars;                       // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;             // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;         // [ACC_STAGES]
+    uint64_t* full_bar = bars;                       // [MAX_STAGES]
+    uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES;     // [ACC_STAGES]
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
     bf16* xch = reinterpret_cast<bf16*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);   // [BLOCK_N][64] (SWIGLU_T only)
@@ -508,7 +513,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     const int grid = tiles < slots ? tiles : slots;
     GemmParams pt = p;
     pt.trace = g_trace;
-    DOTS_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)S::TOTAL, stream, true, ta, tb, pt));
+    const int stages = (p.stages > 0 && p.stages < S::STAGES) ? p.stages : S::STAGES;
+    const size_t smem = (size_t)stages * S::STAGE_BYTES + S::BAR_BYTES + S::XCH_BYTES + 1024;
+    DOTS_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, true, ta, tb, pt));
     return 0;
 }
 
@@ -813,6 +820,7 @@ extern "C" int dots_gemm_skinny_bf16(const void* X, long long ldx, const void* W
     }
     p.m_blocks = (N + BLOCK_M - 1) / BLOCK_M;
     p.n_blocks = 1;
+    p.stages = 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta, tb;
     if (make_tmap_2d_bf16(&ta, W, N, K, ldw, BLOCK_M)) return -4;
@@ -850,6 +858,7 @@ extern "C" int dots_gemm_skinny_swiglu_bf16(const void* X, long long ldx, const 
     p.out = act; p.ldo = ld_act;
     p.m_blocks = two_i / BLOCK_M;
     p.n_blocks = 1;
+    p.stages = 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta, tb;
     if (make_tmap_2d_bf16(&ta, W, two_i, K, ldw, BLOCK_M)) return -4;
@@ -861,6 +870,17 @@ extern "C" int dots_gemm_skinny_swiglu_bf16(const void* X, long long ldx, const 
         case 128: return launch_gemm<128, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
         default: return launch_gemm<256, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
     }
+}
+
+// Ring depth per decode GEMM family (dots_set_decode_stages): [0] split-K partial GEMMs (capped by the k-blocks a CTA owns),
+// [1] gate|up + SwiGLU, [2] lm_head.  Chosen so that consecutive kernels of the step co-reside on an SM (the next kernel's
+// weight prefetch runs under the current kernel's tail): 16 KB of weights + 8 KB of activations per stage at batch 64.
+namespace dots { int g_dec_stages[3] = {4, 5, 4}; }
+
+extern "C" int dots_set_decode_stages(int partial, int swiglu, int head) {
+    DOTS_REQUIRE(partial >= 2 && partial <= 8 && swiglu >= 2 && swiglu <= 8 && head >= 2 && head <= 8, "dots_set_decode_stages: depths must be 2..8");
+    dots::g_dec_stages[0] = partial; dots::g_dec_stages[1] = swiglu; dots::g_dec_stages[2] = head;
+    return 0;
 }
 
 // ---- decode GEMMs over pre-tiled operands (1-D bulk copies; see ops.tile_weight / ops.tile_rows) ----
@@ -883,6 +903,7 @@ extern "C" int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act
     p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
     p.b_tiled = reinterpret_cast<const uint8_t*>(Xt);
     p.out_tiled = 1;
+    p.stages = g_dec_stages[1] < p.num_k_blocks ? g_dec_stages[1] : p.num_k_blocks;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta{}, tb{};            // unused with tiled operands
     return batch <= 32 ? launch_gemm<32, DOTS_EPI_SWIGLU_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_SWIGLU_T>(ta, tb, p, st);
@@ -905,6 +926,7 @@ extern "C" int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_ro
     p.m_blocks = (N + BLOCK_M - 1) / BLOCK_M;
     p.n_blocks = 1;
     p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
+    p.stages = g_dec_stages[2];
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta{}, tb{};
     if (x_tile_rows) p.b_tiled = reinterpret_cast<const uint8_t*>(X);
@@ -933,6 +955,7 @@ extern "C" int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* p
     p.n_blocks = 1;
     p.a_tiled = reinterpret_cast<const uint8_t*>(Wt);
     p.b_tiled = reinterpret_cast<const uint8_t*>(Xt);
+    p.stages = p.kb_per_split < g_dec_stages[0] ? (p.kb_per_split < 2 ? 2 : p.kb_per_split) : g_dec_stages[0];
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap ta{}, tb{};
     return batch <= 32 ? launch_gemm<32, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st) : launch_gemm<64, DOTS_EPI_F32_PARTIAL_T>(ta, tb, p, st);

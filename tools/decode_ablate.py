@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="override the flash-decoding split count of the plan")
     ap.add_argument("--no-cluster", action="store_true", help="combine kernel instead of the cluster merge for 2..4 attention splits")
     ap.add_argument("--quick", action="store_true", help="only the full step and the attention ablation")
+    ap.add_argument("--stages", default=None, help="ring depths partial,swiglu,head of the decode GEMMs (e.g. 4,5,4)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = config.full()
@@ -37,6 +38,8 @@ def main():
     del ck
     if args.no_cluster:
         ops.set_decode_cluster(False)
+    if args.stages:
+        ops.set_decode_stages(*[int(x) for x in args.stages.split(",")])
     B = args.batch
     ctx_max = (args.ctx + args.steps + 2 + 63) // 64 * 64
     kc, vc = eng._alloc_cache(B, ctx_max)
