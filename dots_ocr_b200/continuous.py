@@ -307,3 +307,24 @@ class ContinuousBatcher:
                     self.backend.rearm(list(range(self.backend.n_slots)))
                 except Exception:       # noqa: BLE001
                     pass
+
+
+def serving_front(page_runner, kind: Optional[str] = None, max_batch: int = 64, max_prompt: int = 16384, max_new: int = 8192, chunk: int = 32):
+    """The request front behind the one-page call surface (``inference_with_vllm``, the HTTP endpoint, the per-GPU workers).
+
+    ``kind`` (default: environment ``DOTS_B200_BATCHER``, else ``continuous``):
+      * ``continuous``  ContinuousBatcher over EngineSlots: ``max_batch`` decode slots, finished pages leave and queued pages enter
+                        between chunks of ``chunk`` decode steps (the server-side behaviour the reference's 64-thread fan-out expects
+                        from vLLM, dots_ocr/parser.py:282-290).  ``max_prompt`` / ``max_new`` size the session's KV cache
+                        (28 672 B per token and slot at full size: 64 x 24.6 k tokens = 45 GB of the 180 GB).
+      * ``batching``    BatchingRunner: batches formed at arrival, each run to its longest page.
+    Falls back to ``batching`` for runners that have no CUDA engine (CPU stand-ins in tests)."""
+    import os
+    kind = (kind or os.environ.get("DOTS_B200_BATCHER", "continuous")).lower()
+    eng = getattr(page_runner, "engine", None)
+    if kind == "continuous" and eng is not None and hasattr(eng, "_new_decode_state"):
+        slots = EngineSlots(eng, page_runner.tokenizer, n_slots=min(int(max_batch), 256), max_prompt=max_prompt, max_new=max_new, chunk=chunk,
+                            min_pixels=getattr(page_runner, "min_pixels", None), max_pixels=getattr(page_runner, "max_pixels", None))
+        return ContinuousBatcher(slots)
+    from .batching import BatchingRunner
+    return BatchingRunner(page_runner, max_batch=max_batch)

@@ -544,11 +544,16 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
     const bool live = c < nchunks;
     float x[8];
     float ss = 0.f;
+    uint4 rv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
     if (live) {
+        // the residual row and the norm weight do not depend on the partials: request them first so that the whole kernel is one
+        // round of L2 latency (plus the block reduction)
+        rv = reinterpret_cast<const uint4*>(resid + (long long)b * H)[c];
+        gv = __ldg(reinterpret_cast<const uint4*>(w) + c);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         sum_splits8(partial + (long long)b * H + c * 8, (long long)B * H, splits, acc);
         float rr[8];
-        unpack8(reinterpret_cast<const uint4*>(resid + (long long)b * H)[c], rr);
+        unpack8(rv, rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             x[j] = bf16_round(bf16_round(acc[j]) + rr[j]);
@@ -565,7 +570,7 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
     const float r = rsqrtf(tot / (float)H + eps);
     if (live) {
         float g[8], f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+        unpack8(gv, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = bf16_round(x[j] * r) * g[j];
         bf16* dst = tile_rows > 0 ? normed + tiled_row_off(b, c * 8, tile_rows) : normed + (long long)b * H + c * 8;

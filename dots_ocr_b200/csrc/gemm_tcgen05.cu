@@ -873,9 +873,9 @@ extern "C" int dots_gemm_skinny_swiglu_bf16(const void* X, long long ldx, const 
 }
 
 // Ring depth per decode GEMM family (dots_set_decode_stages): [0] split-K partial GEMMs (capped by the k-blocks a CTA owns),
-// [1] gate|up + SwiGLU, [2] lm_head.  Chosen so that consecutive kernels of the step co-reside on an SM (the next kernel's
-// weight prefetch runs under the current kernel's tail): 16 KB of weights + 8 KB of activations per stage at batch 64.
-namespace dots { int g_dec_stages[3] = {4, 5, 4}; }
+// [1] gate|up + SwiGLU, [2] lm_head; 16 KB of weights + 8 KB of activations per stage at batch 64.  Measured at batch 64 (ablate_r2j_*):
+// 4/4/4 2.059 ms per step, 4/5/4 2.022, 4/6/4 2.019, 3/5/4 2.035, 6/5/4 1.991 (default), 4/5/6 2.024.
+namespace dots { int g_dec_stages[3] = {6, 5, 4}; }
 
 extern "C" int dots_set_decode_stages(int partial, int swiglu, int head) {
     DOTS_REQUIRE(partial >= 2 && partial <= 8 && swiglu >= 2 && swiglu <= 8 && head >= 2 && head <= 8, "dots_set_decode_stages: depths must be 2..8");

@@ -34,13 +34,14 @@ def set_default_runner(runner) -> None:
 
 
 def get_default_runner():
-    """Process-wide runner: the engine behind a request batcher, so that the parser's thread fan-out (one page per call,
-    parser.py:282-290) shares generate() calls the way requests share a vLLM server's batches."""
+    """Process-wide runner: the engine behind a continuous batcher, so that the parser's thread fan-out (one page per call,
+    parser.py:282-290) shares decode steps the way requests share a vLLM server's batches: a page that finishes frees its slot
+    for the next queued page while the others keep decoding."""
     with _lock:
         if _state["runner"] is None:
-            from ..batching import BatchingRunner
+            from ..continuous import serving_front
             from ..runner import PageRunner
-            _state["runner"] = BatchingRunner(PageRunner.from_default())
+            _state["runner"] = serving_front(PageRunner.from_default())       # continuous batching by default (DOTS_B200_BATCHER)
         return _state["runner"]
 
 

@@ -22,10 +22,10 @@ from .batching import page_vit_tokens
 def b200_worker(rank: int, weights_dir: str = "./weights/DotsOCR", preset: Optional[str] = None, max_batch: int = 64):
     """Default worker factory: the engine on ``cuda:<rank>`` behind a request batcher."""
     import torch
-    from .batching import BatchingRunner
+    from .continuous import serving_front
     from .runner import PageRunner
     torch.cuda.set_device(rank)
-    return BatchingRunner(PageRunner.from_default(device=f"cuda:{rank}", weights_dir=weights_dir, preset=preset), max_batch=max_batch)
+    return serving_front(PageRunner.from_default(device=f"cuda:{rank}", weights_dir=weights_dir, preset=preset), max_batch=max_batch)
 
 
 class _Echo:

@@ -530,7 +530,7 @@ def decode_chain(attn, w_o, w_gu, w_down, w_qkv_next, partial, resid, normed, ac
     _lib.check(rc, "dots_decode_chain")
 
 
-def set_decode_stages(partial: int = 4, swiglu: int = 5, head: int = 4) -> None:
+def set_decode_stages(partial: int = 6, swiglu: int = 5, head: int = 4) -> None:
     """Ring depths of the decode GEMM families (tuning; see dots_set_decode_stages)."""
     _lib.check(_lib.load().dots_set_decode_stages(int(partial), int(swiglu), int(head)), "dots_set_decode_stages")
 

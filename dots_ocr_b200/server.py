@@ -9,7 +9,8 @@ point ``--ip/--port`` at a B200 box:
     python -m dots_ocr_b200.server --port 8000 --model-name rednote-hilab/dots.mocr
 
 Only what that client needs is here: ``POST /v1/chat/completions`` (non-streaming), ``GET /v1/models``, ``GET /health``.
-Request threads block on the process-wide ``BatchingRunner`` (``dots_ocr_b200/batching.py``), which groups concurrent pages
+Request threads block on the process-wide request front (``dots_ocr_b200/continuous.py:serving_front``: continuous batching by
+default, ``DOTS_B200_BATCHER=batching`` for arrival-time batches), which groups concurrent pages
 into one ``generate`` call -- the role continuous batching plays inside the vLLM server.  Decoding is greedy
 (BASELINE.json); ``temperature`` / ``top_p`` are accepted and ignored.  Standard library only: no web framework.
 """
@@ -201,9 +202,9 @@ def main(argv: Optional[list] = None) -> None:
         from .multigpu import MultiGpuRunner, b200_worker
         runner = MultiGpuRunner(a.gpus, factory=b200_worker, factory_args=(a.weights_dir, None, a.max_batch))
     else:
-        from .batching import BatchingRunner
+        from .continuous import serving_front
         from .runner import PageRunner
-        runner = BatchingRunner(PageRunner.from_default(device=a.device, weights_dir=a.weights_dir), max_batch=a.max_batch)
+        runner = serving_front(PageRunner.from_default(device=a.device, weights_dir=a.weights_dir), max_batch=a.max_batch)
     srv = make_server(runner, a.host, a.port, a.model_name, quiet=not a.verbose)
     print(f"dots_ocr_b200 serving {a.model_name} on http://{a.host}:{srv.server_address[1]}/v1", flush=True)
     try:

@@ -255,7 +255,7 @@ DOTS_API int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act_t
 DOTS_API int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* partial, int batch, int N, int K, int splits, void* stream);
 
 /* Ring depths (2..8 stages of 16 KB weights + batch-tile activations) of the decode GEMM families: split-K partial GEMMs (additionally
- * capped by the k-blocks one CTA owns), gate|up + SwiGLU, lm_head.  Defaults 4 / 5 / 4: consecutive kernels of a step fit one SM together. */
+ * capped by the k-blocks one CTA owns), gate|up + SwiGLU, lm_head.  Defaults 6 / 5 / 4 (measured best at batch 64). */
 DOTS_API int dots_set_decode_stages(int partial, int swiglu, int head);
 
 /* lm_head of one decode step, batch <= 64: out[b, n] = bf16(X . W^T), row-major.  x_tile_rows = 32 / 64: X is k-block-tiled;
