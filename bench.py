@@ -254,8 +254,11 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG is left as the caller set it (the driver counts ranks in NCCL's INFO log); the JSON line is printed after
-        # the process group is gone so that it stays the LAST line of stdout
+        # NCCL_DEBUG is left as the caller set it; its output is routed to a file (NCCL_DEBUG_FILE, one per process) unless the caller
+        # chose one, because NCCL keeps logging at process exit and the JSON must stay the LAST line of stdout
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     from dots_ocr_b200 import config, weights, ops
@@ -437,7 +440,17 @@ def run_gpu(args):
             "kernels": by_kernel, "ids_checksum": {"value": checksum, "golden": golden, "matches_golden": (checksum == golden) if golden else None},
             "cpu_baseline": cpu}
     if world > 1:
-        time.sleep(1.0)             # let the other ranks' teardown chatter (NCCL INFO) drain: the JSON stays the last stdout line
+        # NCCL's log of this run (routed to files above) is echoed on STDERR so that whoever reads the run's output still sees the
+        # communicator's rank count; stdout carries nothing after the JSON line
+        if str(os.environ.get("NCCL_DEBUG_FILE", "")).startswith(os.path.join(ROOT, "gpurun_out", "nccl_debug.")):
+            import glob
+            for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"nccl_debug.*.{os.getpid()}.log"))):
+                try:
+                    with open(f) as fh:
+                        sys.stderr.write(fh.read())
+                except OSError:
+                    pass
+            sys.stderr.flush()
     print(json.dumps(line), flush=True)
 
 

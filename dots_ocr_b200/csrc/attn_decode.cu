@@ -176,6 +176,33 @@ attn_decode_kernel(const DecParams p) {
     }
 
     // =============================== consumer warps ===============================
+    // Fused QKV finalize, one (head, 4-column pair) unit per thread.  Everything that does not depend on this layer's QKV GEMM --
+    // the bias, the rotary angle and its bf16-rounded cos / sin (the slow accurate cosf / sinf) -- is fetched and computed BEFORE the
+    // dependency wait, i.e. while that GEMM is still running; after the wait the partials of all splits are requested at once, so the
+    // prologue is one round of L2 latency instead of four.
+    const int N = (p.n_q_heads + 2 * p.n_kv_heads) * DEC_D;
+    const int n_units = (p.group + 2) * 16;                                // group <= 8: at most 160 units for 256 consumer threads
+    const int hl = tid >> 4, c4 = tid & 15;
+    const bool has_unit = fused && tid < n_units && (hl < p.group || holds_new);     // k / v rows only in the split that holds the new key
+    const int col0 = (hl < p.group ? (kvh * p.group + hl) : (hl == p.group ? p.n_q_heads + kvh : p.n_q_heads + p.n_kv_heads + kvh)) * DEC_D + c4 * 4;
+    int posb = 0;
+    uint2 b1 = make_uint2(0, 0), b2 = make_uint2(0, 0);
+    float cs[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_unit) {
+        posb = p.pos[b];                                                    // requires pos[b] == ctx_len[b] - 1
+        if (p.qkv_bf16 == nullptr) {
+            b1 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0);
+            b2 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0 + 64);
+        }
+        if (hl <= p.group) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float ang = __fmul_rn((float)posb, p.inv_freq[c4 * 4 + j]);
+                cs[j] = bf16_round(cosf(ang));
+                sn[j] = bf16_round(sinf(ang));
+            }
+        }
+    }
     pdl_wait();
 
     // Q tile: rows 0..G-1 = the group's q heads, rows G..15 zero
@@ -188,21 +215,12 @@ attn_decode_kernel(const DecParams p) {
             *reinterpret_cast<uint4*>(sQ + swz128(r, c)) = val;
         }
     } else {
-        // ---- fused QKV finalize: split-K reduce (fixed order) + bias + RoPE; q -> sQ, k/v -> cache row `pos` ----
+        // ---- split-K reduce (fixed order) + bias + RoPE; q -> sQ, k/v -> cache row `pos` ----
         for (int idx = tid; idx < (16 - p.group) * 16; idx += DEC_WARPS * 32) {
             const int r = p.group + (idx >> 4), c = idx & 15;
             *reinterpret_cast<uint4*>(sQ + swz128(r, c)) = make_uint4(0, 0, 0, 0);
         }
-        const int posb = p.pos[b];
-        const bool owns_new = holds_new;                                   // requires pos[b] == ctx_len[b] - 1
-        const int N = (p.n_q_heads + 2 * p.n_kv_heads) * DEC_D;
-        const long long sstride = (long long)(gridDim.z) * N;
-        const int n_units = (p.group + 2) * 16;                            // (head, 4-column pair chunk)
-        for (int u = tid; u < n_units; u += DEC_WARPS * 32) {
-            const int hl = u >> 4, c4 = u & 15;
-            if (hl >= p.group && !owns_new) continue;
-            const int col0 = (hl < p.group ? (kvh * p.group + hl)
-                                           : (hl == p.group ? p.n_q_heads + kvh : p.n_q_heads + p.n_kv_heads + kvh)) * DEC_D + c4 * 4;
+        if (has_unit) {
             float x1[4], x2[4];
             if (p.qkv_bf16 != nullptr) {
                 // q|k|v row of dots_decode_gemm_qkv: reduced, bias added and rounded to bf16 already (HF's Linear output)
@@ -212,30 +230,24 @@ attn_decode_kernel(const DecParams p) {
                 x2[0] = bf16_lo(d.x); x2[1] = bf16_hi(d.x); x2[2] = bf16_lo(d.y); x2[3] = bf16_hi(d.y);
             } else {
                 const float* src = p.qkv_partial + (long long)b * N + col0;
+                const long long sstride = (long long)(gridDim.z) * N;
                 x1[0] = x1[1] = x1[2] = x1[3] = 0.f;
                 x2[0] = x2[1] = x2[2] = x2[3] = 0.f;
-                int sidx = 0;
-                for (; sidx + 4 <= p.qkv_splits; sidx += 4) {
-                    float4 a[4], d[4];
+                for (int s0 = 0; s0 < p.qkv_splits; s0 += 8) {             // 8 splits = 16 loads in flight; adds stay in split order
+                    float4 a[8], d[8];
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        a[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride);
-                        d[w] = *reinterpret_cast<const float4*>(src + (sidx + w) * sstride + 64);
-                    }
+                    for (int w = 0; w < 8; ++w)
+                        if (s0 + w < p.qkv_splits) {
+                            a[w] = *reinterpret_cast<const float4*>(src + (s0 + w) * sstride);
+                            d[w] = *reinterpret_cast<const float4*>(src + (s0 + w) * sstride + 64);
+                        }
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        x1[0] += a[w].x; x1[1] += a[w].y; x1[2] += a[w].z; x1[3] += a[w].w;
-                        x2[0] += d[w].x; x2[1] += d[w].y; x2[2] += d[w].z; x2[3] += d[w].w;
-                    }
+                    for (int w = 0; w < 8; ++w)
+                        if (s0 + w < p.qkv_splits) {
+                            x1[0] += a[w].x; x1[1] += a[w].y; x1[2] += a[w].z; x1[3] += a[w].w;
+                            x2[0] += d[w].x; x2[1] += d[w].y; x2[2] += d[w].z; x2[3] += d[w].w;
+                        }
                 }
-                for (; sidx < p.qkv_splits; ++sidx) {
-                    const float4 a = *reinterpret_cast<const float4*>(src + sidx * sstride);
-                    const float4 d = *reinterpret_cast<const float4*>(src + sidx * sstride + 64);
-                    x1[0] += a.x; x1[1] += a.y; x1[2] += a.z; x1[3] += a.w;
-                    x2[0] += d.x; x2[1] += d.y; x2[2] += d.z; x2[3] += d.w;
-                }
-                const uint2 b1 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0);
-                const uint2 b2 = *reinterpret_cast<const uint2*>(p.qkv_bias + col0 + 64);
                 x1[0] = bf16_round(x1[0] + bf16_lo(b1.x)); x1[1] = bf16_round(x1[1] + bf16_hi(b1.x));
                 x1[2] = bf16_round(x1[2] + bf16_lo(b1.y)); x1[3] = bf16_round(x1[3] + bf16_hi(b1.y));
                 x2[0] = bf16_round(x2[0] + bf16_lo(b2.x)); x2[1] = bf16_round(x2[1] + bf16_hi(b2.x));
@@ -243,7 +255,12 @@ attn_decode_kernel(const DecParams p) {
             }
             float o1[4], o2[4];
             if (hl <= p.group) {
-                dec_rope_bf16_4(x1, x2, posb, p.inv_freq, c4 * 4, o1, o2);
+                // HF Qwen2 RoPE rounding points ([Q]:102-146): cos / sin are bf16, every product and the sum round to bf16
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    o1[j] = bf16_round(__fadd_rn(bf16_round(__fmul_rn(x1[j], cs[j])), bf16_round(__fmul_rn(-x2[j], sn[j]))));
+                    o2[j] = bf16_round(__fadd_rn(bf16_round(__fmul_rn(x2[j], cs[j])), bf16_round(__fmul_rn(x1[j], sn[j]))));
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { o1[j] = x1[j]; o2[j] = x2[j]; }
