@@ -406,15 +406,16 @@ attn_decode_kernel(const DecParams p) {
         sML[(warp * 8 + g) * 2 + 1] = l_run[0];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");
-    // the first DEC_D consumer threads finish: thread c owns head dim c of every q head r of the group
-    static_assert(DEC_WARPS * 32 >= DEC_D && DEC_WARPS * 8 * (DEC_D + 2) * 4 <= DEC_STAGES * DEC_STAGE_BYTES, "merge scratch lives in the ring");
-    const int c = tid;
-    const bool finisher = tid < DEC_D;
+    // every consumer thread finishes: thread (c = tid % 128, part = tid / 128) owns head dim c of the q heads r with r % PARTS == part
+    static_assert(DEC_WARPS * 32 % DEC_D == 0 && DEC_WARPS * 8 * (DEC_D + 2) * 4 <= DEC_STAGES * DEC_STAGE_BYTES, "merge scratch lives in the ring");
+    constexpr int PARTS = DEC_WARPS * 32 / DEC_D;
+    const int c = tid % DEC_D, part = tid / DEC_D;
+    const bool finisher = true;
     float accv[8], mv[8], lv[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         accv[r] = 0.f; mv[r] = -INFINITY; lv[r] = 0.f;
-        if (finisher && r < p.group) {
+        if (r % PARTS == part && r < p.group) {
             float m = -INFINITY;
 #pragma unroll
             for (int w = 0; w < DEC_WARPS; ++w) m = fmaxf(m, sML[(w * 8 + r) * 2]);
@@ -432,7 +433,7 @@ attn_decode_kernel(const DecParams p) {
     if (p.n_splits == 1) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-            if (finisher && r < p.group)
+            if (r % PARTS == part && r < p.group)
                 p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
     } else if (p.cluster_merge) {
         // ---- on-chip merge across the cluster: peers write (O, m, l) into the leader's shared memory, the leader combines
@@ -441,11 +442,11 @@ attn_decode_kernel(const DecParams p) {
             const uint32_t base = mapa_shared(smem_u32(sMerge + (size_t)(split - 1) * DEC_MERGE_BYTES), 0);
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-                if (r < p.group) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(r * DEC_D + c) * 4), "f"(accv[r]) : "memory");
+                if (r % PARTS == part && r < p.group) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(r * DEC_D + c) * 4), "f"(accv[r]) : "memory");
             if (c == 0) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
-                    if (r < p.group) {
+                    if (r % PARTS == part && r < p.group) {
                         asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(8 * DEC_D + r * 2) * 4), "f"(mv[r]) : "memory");
                         asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(base + (uint32_t)(8 * DEC_D + r * 2 + 1) * 4), "f"(lv[r]) : "memory");
                     }
@@ -455,7 +456,7 @@ attn_decode_kernel(const DecParams p) {
         if (split == 0 && finisher) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                if (r >= p.group) continue;
+                if (r >= p.group || r % PARTS != part) continue;
                 float m = mv[r];
                 for (int sp = 1; sp < p.n_splits; ++sp)
                     m = fmaxf(m, reinterpret_cast<const float*>(sMerge + (size_t)(sp - 1) * DEC_MERGE_BYTES)[8 * DEC_D + r * 2]);
@@ -478,7 +479,7 @@ attn_decode_kernel(const DecParams p) {
     } else if (finisher) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            if (r >= p.group) continue;
+            if (r >= p.group || r % PARTS != part) continue;
             const long long pi = ((long long)b * p.n_q_heads + kvh * p.group + r) * p.n_splits + split;
             p.part_o[pi * DEC_D + c] = accv[r];
             if (c == 0) { p.part_ml[pi * 2] = mv[r]; p.part_ml[pi * 2 + 1] = lv[r]; }

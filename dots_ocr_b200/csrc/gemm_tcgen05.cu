@@ -212,17 +212,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int row,
     } else if constexpr (EPI == DOTS_EPI_F32_PARTIAL_T) {
         // swap-AB decode GEMM: A rows are output features, B rows are batch rows.
         // partial[split][b][feature] fp32; lanes write consecutive features (coalesced).
+        // (this epilogue is the exposed tail of a 3-12 k-block kernel: one base pointer, pointer bumps, no per-element bound
+        // arithmetic on full chunks)
         float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll 1
         for (int c = eg; c < BLOCK_N / 32; c += EPI_GROUPS) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(t_row + c * 32, v);
+            const int b0 = n_blk * BLOCK_N + c * 32;
+            float* dst = out + ((long long)split * p.N + b0) * p.ldo + row;
+            const int nb = min(32, p.N - b0);
             tmem_ld_wait();
             if (row < p.M) {
+                if (nb == 32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int b = n_blk * BLOCK_N + c * 32 + j;
-                    if (b < p.N) out[((long long)split * p.N + b) * p.ldo + row] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) { *dst = __uint_as_float(v[j]); dst += p.ldo; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { if (j < nb) *dst = __uint_as_float(v[j]); dst += p.ldo; }
                 }
             }
         }
