@@ -314,15 +314,22 @@ def run_gpu(args):
         out = eng.generate(idd, pages_u8=pgs, max_new_tokens=N)
         last["u8_ids"] = out.sequences[:, idd.shape[1]:].cpu()
 
+    per_step = {}
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks = []
         for _ in range(k):
             fn()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        # per-step times of this rank (diagnostic only: the reported number is the whole region, max over ranks)
+        per_step[fn.__name__] = [round(a.elapsed_time(b), 1) for a, b in zip([e0] + marks[:-1], marks)]
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -436,7 +443,7 @@ def run_gpu(args):
                        "input": "raw uint8 pages on pinned host memory; resize + rescale + normalise + patchify on the GPU"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm, "roofline_vit_attention": roof_attn,
             "phases_ms": {"decode_loop": round(dec_ms_per_step_total, 2), "step": round(ms_total / args.steps, 2),
-                          "instrumented_step": round(ms_prof, 2)},
+                          "instrumented_step": round(ms_prof, 2), "per_step_rank0": per_step},
             "kernels": by_kernel, "ids_checksum": {"value": checksum, "golden": golden, "matches_golden": (checksum == golden) if golden else None},
             "cpu_baseline": cpu}
     if world > 1:

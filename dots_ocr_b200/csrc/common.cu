@@ -21,6 +21,7 @@ int num_sms() {
     static int cache[64] = {0};          // per device: one process may drive several GPUs
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (g_sm_override[dev] > 0) return g_sm_override[dev];      // launches aimed at an SM partition (dots_set_sm_count)
     if (cache[dev] == 0) {
         int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;

@@ -12,7 +12,10 @@ typedef __nv_bfloat16 bf16;
 
 // Error plumbing: every C-ABI entry returns 0 or a negative code; text via dots_last_error().
 void set_error(const char* fmt, ...);
+// SMs that the next launches may use: the device's count, or the size of the SM partition the caller is feeding
+// (dots_set_sm_count; persistent kernels size their grids with it).
 int num_sms();
+extern int g_sm_override[64];
 // Per-device one-time setup (cudaFuncSetAttribute is per device): true the first time it is called on the current device
 // with this flag array.
 bool first_use_on_device(bool (&flags)[64]);

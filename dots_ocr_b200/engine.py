@@ -176,6 +176,7 @@ class Engine:
         #   "perop"  7 kernels per layer over row-major operands and tensor-map copies; the only mode for batches of 65..256
         self.decode_mode = "tiled"
         self.attn_splits = 0            # 0: planned from the batch size; n: force n key splits in decode attention (tuning runs)
+        self.decode_sms = 0             # 0: plan the decode step for the whole device; n: for an SM partition of n SMs (pipeline.py)
         self._fused_ok: Dict[int, bool] = {}
         self._dec_cache: Optional[dict] = None
         self._cap_stream = torch.cuda.Stream(device=dev)
@@ -336,19 +337,20 @@ class Engine:
         tiles = lambda n: -(-n // 128)
         pairs = max(1, B * t.num_key_value_heads)
         mode = self._mode_for(B)
+        sms = int(self.decode_sms) or self.sms
         if self.attn_splits:
             attn = int(self.attn_splits)
         else:
             # one CTA per (sequence, kv head) once that alone covers most SMs; flash-decoding splits below (<= 4 merge inside a
             # cluster, more go through the combine kernel)
             # (the attention CTA keeps a 128 KB K/V ring: one CTA per SM)
-            attn = 1 if pairs >= (3 * self.sms) // 4 else max(1, min(16, self.sms // pairs))
+            attn = 1 if pairs >= (3 * sms) // 4 else max(1, min(16, sms // pairs))
         return dict(
             mode=mode, fused=(mode == "fused"),
-            qkv=ops.pick_splits(tiles(qkv_n), kb(H), self.sms),
-            o=ops.pick_splits(tiles(H), kb(t.num_attention_heads * t.head_dim), self.sms),
-            gu=ops.pick_splits(tiles(2 * I), kb(H), self.sms),
-            down=ops.pick_splits(tiles(H), kb(I), self.sms),
+            qkv=ops.pick_splits(tiles(qkv_n), kb(H), sms),
+            o=ops.pick_splits(tiles(H), kb(t.num_attention_heads * t.head_dim), sms),
+            gu=ops.pick_splits(tiles(2 * I), kb(H), sms),
+            down=ops.pick_splits(tiles(H), kb(I), sms),
             attn=attn,
         )
 
@@ -510,7 +512,7 @@ class Engine:
         # KV cache, decode workspaces and the captured decode graph are kept from call to call when the shape key repeats
         # (a serving loop and the benchmark call generate with the same batch geometry over and over)
         stops_key = tuple(stop_list(eos_token_id)[: ops.MAX_STOP_IDS])
-        key = (B, ctx_max, N, stops_key, int(pad_token_id), self.decode_mode, self.attn_splits, ops.DECODE_CLUSTER)
+        key = (B, ctx_max, N, stops_key, int(pad_token_id), self.decode_mode, self.attn_splits, ops.DECODE_CLUSTER, int(self.decode_sms))
         ent = self._dec_cache if (self._dec_cache is not None and self._dec_cache["key"] == key and forced_ids is None) else None
         if ent is None:
             self._dec_cache = None                      # release the previous geometry's buffers before allocating new ones

@@ -485,6 +485,43 @@ def set_decode_cluster(enable: bool) -> None:
     _lib.check(_lib.load().dots_set_decode_cluster(int(bool(enable))), "dots_set_decode_cluster")
 
 
+def partition(sms_first: int):
+    """Split the current device's SMs into a first group of ``sms_first`` (multiple of 8) and the rest (CUDA green contexts).
+    Returns ``(stream_first, stream_rest, n_first, n_rest)``: torch streams whose kernels run on their own SMs only."""
+    s0, s1 = _vp(0), _vp(0)
+    n0, n1 = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().dots_partition_create(int(sms_first), C.byref(s0), C.byref(s1), C.byref(n0), C.byref(n1)), "dots_partition_create")
+    dev = torch.cuda.current_device()
+    return (torch.cuda.ExternalStream(s0.value, device=dev), torch.cuda.ExternalStream(s1.value, device=dev), int(n0.value), int(n1.value))
+
+
+def partition_destroy() -> None:
+    _lib.check(_lib.load().dots_partition_destroy(), "dots_partition_destroy")
+
+
+def set_sm_count(n: int) -> None:
+    """Persistent kernels launched next size their grids for ``n`` SMs (an SM partition); 0 = the whole device."""
+    _lib.check(_lib.load().dots_set_sm_count(int(n)), "dots_set_sm_count")
+
+
+class on_partition:
+    """``with on_partition(stream, n_sms):`` -- C-ABI launches and torch ops inside go to that partition's stream, grids sized for it."""
+
+    def __init__(self, stream, n_sms: int):
+        self.stream, self.n = stream, int(n_sms)
+        self._ctx = None
+
+    def __enter__(self):
+        self._ctx = torch.cuda.stream(self.stream)
+        self._ctx.__enter__()
+        set_sm_count(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        set_sm_count(0)
+        return self._ctx.__exit__(*exc)
+
+
 def debug_set_trace(buf: Optional[torch.Tensor]) -> None:
     """Arm (int64 CUDA tensor: [0] = 0, [1] = capacity in records, 3 words per record after that) or disarm (None) the kernel timeline."""
     if buf is not None:

@@ -266,6 +266,19 @@ DOTS_API int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_rows
 /* Number of 8-CTA clusters of dots_decode_gemm_resnorm the current device keeps resident at once. */
 DOTS_API int dots_decode_gemm_max_clusters(int batch, int* out);
 
+/* ---- SM partitions (two phases of the page pipeline side by side on one GPU) -------------------
+ * dots_partition_create splits the current device's SMs into a first group of `sms_first` SMs (a multiple of 8; it keeps the
+ * thread-block-cluster guarantees, so the CTA-pair prefill GEMMs go there) and the rest, as two CUDA green contexts, and returns
+ * one non-blocking stream in each (usable wherever this header takes a `void* stream`, and by the CUDA runtime of the caller) plus
+ * the SM counts the driver actually provisioned.  Kernels launched into such a stream run on its SMs only.  One partition per
+ * device; dots_partition_destroy synchronises the device and releases it (safe to call when none exists).
+ * dots_set_sm_count(n): the persistent kernels launched next (by this host thread's calls, on the current device) size their
+ * grids for n SMs instead of the whole device; 0 restores the device count.  Set it to a partition's count before feeding that
+ * partition's stream. */
+DOTS_API int dots_partition_create(int sms_first, void** stream_first, void** stream_rest, int* n_first, int* n_rest);
+DOTS_API int dots_partition_destroy(void);
+DOTS_API int dots_set_sm_count(int n);
+
 /* ---- CUDA-graph helpers (the decode step is captured once and replayed) ----------------------- */
 DOTS_API int dots_graph_begin(void* stream);
 DOTS_API int dots_graph_end(void* stream, void** graph_exec_out);
