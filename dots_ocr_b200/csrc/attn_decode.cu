@@ -101,7 +101,14 @@ __device__ __forceinline__ long long dec_out_off(const DecParams& p, int b, int 
     return p.out_tile_rows > 0 ? tiled_row_off(b, col, p.out_tile_rows) : (long long)b * p.n_q_heads * DEC_D + col;
 }
 
+#ifndef DEC_MAXNREG
+#define DEC_MAXNREG 0
+#endif
+#if DEC_MAXNREG > 0
+__global__ void __maxnreg__(DEC_MAXNREG)
+#else
 __global__ void __launch_bounds__(DEC_THREADS)
+#endif
 attn_decode_kernel(const DecParams p) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
