@@ -542,6 +542,8 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
     if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              DEC_SMEM + (DEC_MAX_CLUSTER - 1) * DEC_MERGE_BYTES));
+        DOTS_CHECK_CUDA(prefer_max_shared(attn_decode_kernel));
+        DOTS_CHECK_CUDA(prefer_max_shared(attn_decode_combine_kernel));
     }
     DOTS_REQUIRE(p.ctx_max % DEC_RING_KEYS == 0, "%s: ctx_max must be a multiple of %d (the cache is stored in 64-key tiles)", who, DEC_RING_KEYS);
     DOTS_REQUIRE(p.out_tile_rows == 0 || (p.out_tile_rows % 8 == 0 && batch <= p.out_tile_rows), "%s: bad out_tile_rows %d", who, p.out_tile_rows);
