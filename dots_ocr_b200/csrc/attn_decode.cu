@@ -101,14 +101,7 @@ __device__ __forceinline__ long long dec_out_off(const DecParams& p, int b, int 
     return p.out_tile_rows > 0 ? tiled_row_off(b, col, p.out_tile_rows) : (long long)b * p.n_q_heads * DEC_D + col;
 }
 
-#ifndef DEC_MAXNREG
-#define DEC_MAXNREG 0
-#endif
-#if DEC_MAXNREG > 0
-__global__ void __maxnreg__(DEC_MAXNREG)
-#else
 __global__ void __launch_bounds__(DEC_THREADS)
-#endif
 attn_decode_kernel(const DecParams p) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
@@ -542,8 +535,6 @@ static int launch_attn_decode(DecParams& p, int batch, int n_q_heads, int n_kv_h
     if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              DEC_SMEM + (DEC_MAX_CLUSTER - 1) * DEC_MERGE_BYTES));
-        DOTS_CHECK_CUDA(prefer_max_shared(attn_decode_kernel));
-        DOTS_CHECK_CUDA(prefer_max_shared(attn_decode_combine_kernel));
     }
     DOTS_REQUIRE(p.ctx_max % DEC_RING_KEYS == 0, "%s: ctx_max must be a multiple of %d (the cache is stored in 64-key tiles)", who, DEC_RING_KEYS);
     DOTS_REQUIRE(p.out_tile_rows == 0 || (p.out_tile_rows % 8 == 0 && batch <= p.out_tile_rows), "%s: bad out_tile_rows %d", who, p.out_tile_rows);

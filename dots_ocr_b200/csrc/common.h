@@ -46,20 +46,6 @@ bool first_use_on_device(bool (&flags)[64]);
         }                                                                                  \
     } while (0)
 
-// Kernels of the decode step follow each other within microseconds and overlap through programmatic dependent launch: a CTA of
-// kernel N+1 can only join an SM that still runs kernel N if the SM's L1 / shared-memory split already leaves room for it, and that
-// split is only re-chosen on an idle SM.  Every kernel of the chain therefore asks for the largest shared-memory carve-out, whatever
-// its own footprint, so the split never has to change (build with -DDOTS_NO_CARVEOUT to measure the difference).
-template <typename Kern>
-inline cudaError_t prefer_max_shared(Kern kern) {
-#ifdef DOTS_NO_CARVEOUT
-    (void)kern;
-    return cudaSuccess;
-#else
-    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-#endif
-}
-
 // Programmatic dependent launch (PDL): kernels launched through launch_ex(..., pdl=true) may start while their stream
 // predecessor is still running; they call pdl_wait() (ptx.cuh) before touching anything a predecessor writes.
 // dots_set_pdl(0) turns the attribute off globally (plain stream serialisation).

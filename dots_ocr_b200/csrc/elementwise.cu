@@ -770,10 +770,6 @@ extern "C" int dots_argmax_advance(const void* logits, long long ldl, int batch,
     StopIds stops{};
     stops.n = n_stops;
     for (int i = 0; i < n_stops; ++i) stops.id[i] = stop_ids[i];
-    {
-        static bool configured[64] = {false};
-        if (first_use_on_device(configured)) DOTS_CHECK_CUDA(prefer_max_shared(argmax_advance_kernel));
-    }
     DOTS_CHECK_CUDA(launch_ex(argmax_advance_kernel, dim3(batch), dim3(1024), (size_t)(0), ST(stream), true, (const bf16*)logits, ldl, vocab, next_ids, out_ids, out_ld, step, pos, ctx_len, finished, stops, pad_id, forced_ids, forced_ld));
     return 0;
 }
@@ -784,10 +780,6 @@ extern "C" int dots_decode_embed_rmsnorm(const long long* ids, const void* table
     DOTS_REQUIRE(batch > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_embed_rmsnorm: H %% 8, H <= 2048");
     DOTS_REQUIRE(n_counters >= 0 && (n_counters == 0 || counters), "dots_decode_embed_rmsnorm: n_counters without a counter array");
     DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && H % 64 == 0), "dots_decode_embed_rmsnorm: bad tile_rows %d", tile_rows);
-    {
-        static bool configured[64] = {false};
-        if (first_use_on_device(configured)) DOTS_CHECK_CUDA(prefer_max_shared(decode_embed_rmsnorm_kernel));
-    }
     DOTS_CHECK_CUDA(launch_ex(decode_embed_rmsnorm_kernel, dim3((batch + 7) / 8), dim3(256), (size_t)(0), ST(stream), true, ids, (const bf16*)table, vocab, (const bf16*)w, (bf16*)resid, (bf16*)normed, batch, H, eps, counters, n_counters, tile_rows));
     return 0;
 }
@@ -797,10 +789,6 @@ extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, vo
     DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
     DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && H % 64 == 0), "dots_decode_residual_rmsnorm: bad tile_rows %d", tile_rows);
     const int threads = ((H / 8) + 31) / 32 * 32;
-    {
-        static bool configured[64] = {false};
-        if (first_use_on_device(configured)) DOTS_CHECK_CUDA(prefer_max_shared(decode_residual_rmsnorm_kernel));
-    }
     DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps, tile_rows, g_trace));
     return 0;
 }

@@ -514,7 +514,6 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     static bool configured[64] = {false};
     if (first_use_on_device(configured)) {
         DOTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        DOTS_CHECK_CUDA(prefer_max_shared(kern));
     }
     const int tiles = p.m_blocks * p.n_blocks * p.splits;
     const int slots = num_sms() * S::MIN_CTAS;

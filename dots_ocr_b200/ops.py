@@ -485,17 +485,33 @@ def set_decode_cluster(enable: bool) -> None:
     _lib.check(_lib.load().dots_set_decode_cluster(int(bool(enable))), "dots_set_decode_cluster")
 
 
+_PARTITIONS = {}      # device index -> (sms_first, stream_first, stream_rest, n_first, n_rest)
+
+
 def partition(sms_first: int):
     """Split the current device's SMs into a first group of ``sms_first`` (multiple of 8) and the rest (CUDA green contexts).
-    Returns ``(stream_first, stream_rest, n_first, n_rest)``: torch streams whose kernels run on their own SMs only."""
+    Returns ``(stream_first, stream_rest, n_first, n_rest)``: torch streams whose kernels run on their own SMs only.
+
+    The partition lives as long as the process: torch's allocators remember every stream a tensor was used on (a pinned host
+    buffer copied on a partition stream gets an event recorded on that stream when it is freed), so the streams must not die
+    before the tensors do.  Asking again for the same split returns the same streams; a different split needs an explicit
+    ``partition_destroy()`` first (only safe once nothing that touched the old streams is alive)."""
+    dev = torch.cuda.current_device()
+    have = _PARTITIONS.get(dev)
+    if have is not None:
+        if have[0] != int(sms_first):
+            raise RuntimeError(f"device {dev} is already split {have[3]} + {have[4]} SMs; partition_destroy() before asking for {sms_first}")
+        return have[1:]
     s0, s1 = _vp(0), _vp(0)
     n0, n1 = C.c_int(0), C.c_int(0)
     _lib.check(_lib.load().dots_partition_create(int(sms_first), C.byref(s0), C.byref(s1), C.byref(n0), C.byref(n1)), "dots_partition_create")
-    dev = torch.cuda.current_device()
-    return (torch.cuda.ExternalStream(s0.value, device=dev), torch.cuda.ExternalStream(s1.value, device=dev), int(n0.value), int(n1.value))
+    ent = (int(sms_first), torch.cuda.ExternalStream(s0.value, device=dev), torch.cuda.ExternalStream(s1.value, device=dev), int(n0.value), int(n1.value))
+    _PARTITIONS[dev] = ent
+    return ent[1:]
 
 
 def partition_destroy() -> None:
+    _PARTITIONS.pop(torch.cuda.current_device(), None)
     _lib.check(_lib.load().dots_partition_destroy(), "dots_partition_destroy")
 
 

@@ -46,8 +46,7 @@ class PagePipeline:
         self.closed = True
         with torch.cuda.device(self.eng.device):
             torch.cuda.synchronize()
-            self.slots = [None, None]                            # graphs and state buffers go before their streams
-            ops.partition_destroy()
+            self.slots = [None, None]          # KV caches, decode state, graphs.  The SM partition itself stays (ops.partition)
 
     def __enter__(self):
         return self

@@ -10,10 +10,9 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def parts():
     from dots_ocr_b200 import ops
-    sp, sd, n_p, n_d = ops.partition(96)
+    sp, sd, n_p, n_d = ops.partition(96)          # process-lifetime (ops.partition): the pipeline tests reuse the same split
     yield sp, sd, n_p, n_d
     torch.cuda.synchronize()
-    ops.partition_destroy()
 
 
 def test_partition_sizes_and_results(parts):
@@ -77,3 +76,11 @@ def test_partitions_run_concurrently(parts):
     both = max(ea[0].elapsed_time(eb[1]), ea[0].elapsed_time(ea[1]))
     print(f"alone {t_p:.2f} + {t_d:.2f} ms, together {both:.2f} ms")
     assert both < 0.8 * (t_p + t_d)
+
+
+def test_partition_is_cached_and_a_second_split_is_refused(parts):
+    from dots_ocr_b200 import ops
+    again = ops.partition(96)
+    assert again[0] is parts[0] and again[2:] == parts[2:]
+    with pytest.raises(RuntimeError):
+        ops.partition(64)

@@ -174,6 +174,7 @@ def main():
     res["projection"] = {"vit_64_pages_ms": round(per_page_vit * 64, 1), "decode_511_steps_ms": round((res["both_decode_ms"] or 0) * 511, 1)}
     print(json.dumps(res), flush=True)
     del g_d, g_full
+    torch.cuda.synchronize()
     ops.partition_destroy()
 
 
