@@ -534,8 +534,15 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
                                                                       bf16* __restrict__ normed, int B, int H, float eps, int tile_rows,
                                                                       unsigned long long* trace) {
     if (threadIdx.x == 0) trace_point(trace, 30, 0);
+#ifdef DOTS_RESNORM_EARLY_TRIGGER
+    // the successor (a GEMM) only prefetches immutable weights ahead of ITS dependency wait, so it may start while this kernel is
+    // still waiting for the split-K partials
+    pdl_launch_dependents();
+    pdl_wait();
+#else
     pdl_wait();
     pdl_launch_dependents();
+#endif
     if (threadIdx.x == 0) trace_point(trace, 30, 1);
     __shared__ float s_part[8];
     const int b = blockIdx.x;
