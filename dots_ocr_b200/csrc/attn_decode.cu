@@ -205,8 +205,8 @@ attn_decode_kernel(const DecParams p) {
         }
     }
     if (p.dep.wait_ctr != nullptr) {
-        if (lane == 0) dep_wait(p.dep.wait_ctr, p.dep.wait_target);        // the q|k|v GEMM's partials are complete
-        __syncwarp();
+        if (tid == 0) dep_wait(p.dep.wait_ctr, p.dep.wait_target);         // the q|k|v GEMM's partials are complete
+        asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");  // one poller per CTA, the consumer warps follow it
     } else {
         pdl_wait();
     }
@@ -441,7 +441,11 @@ attn_decode_kernel(const DecParams p) {
         for (int r = 0; r < 8; ++r)
             if (r % PARTS == part && r < p.group)
                 p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
-        if (p.dep.signal_ctr != nullptr) dep_signal_warp(p.dep.signal_ctr, lane);         // DEC_WARPS signals per CTA
+        if (p.dep.signal_ctr != nullptr) {                                                // one signal per CTA
+            dep_publish();
+            asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");
+            if (tid == 0) dep_signal(p.dep.signal_ctr);
+        }
     } else if (p.cluster_merge) {
         // ---- on-chip merge across the cluster: peers write (O, m, l) into the leader's shared memory, the leader combines
         //      in split order (same arithmetic as attn_decode_combine_kernel) ----

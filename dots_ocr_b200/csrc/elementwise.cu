@@ -540,8 +540,8 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
                                                                       unsigned long long* trace, const DepSpec dep) {
     if (threadIdx.x == 0) trace_point(trace, 30, 0);
     if (dep.wait_ctr != nullptr) {
-        if ((threadIdx.x & 31) == 0) dep_wait(dep.wait_ctr, dep.wait_target);     // the split-K partials are complete
-        __syncwarp();
+        if (threadIdx.x == 0) dep_wait(dep.wait_ctr, dep.wait_target);            // the split-K partials are complete
+        __syncthreads();
     } else {
         pdl_wait();
     }
@@ -587,7 +587,11 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
         bf16* dst = tile_rows > 0 ? normed + tiled_row_off(b, c * 8, tile_rows) : normed + (long long)b * H + c * 8;
         *reinterpret_cast<uint4*>(dst) = pack8(f);
     }
-    if (dep.signal_ctr != nullptr) dep_signal_warp(dep.signal_ctr, threadIdx.x & 31);        // blockDim.x / 32 signals per CTA
+    if (dep.signal_ctr != nullptr) {                                                       // one signal per CTA
+        dep_publish();
+        __syncthreads();
+        if (threadIdx.x == 0) dep_signal(dep.signal_ctr);
+    }
     if (threadIdx.x == 0) trace_point(trace, 30, 4);
 }
 

@@ -492,7 +492,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
 
             gemm_epilogue_tile<BLOCK_N, EPI>(p, row, m_blk, n_blk, split, t_row, eg, wq, lane, xch);
-            if (p.dep.signal_ctr != nullptr) dep_signal_warp(p.dep.signal_ctr, lane);      // 4 * EPI_GROUPS signals per tile
+            if (p.dep.signal_ctr != nullptr) {                                            // one signal per tile
+                dep_publish();
+                asm volatile("bar.sync 3, %0;" ::"n"(128 * EPI_GROUPS) : "memory");      // all epilogue warps have stored and fenced
+                if (threadIdx.x == 128) dep_signal(p.dep.signal_ctr);
+            }
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();

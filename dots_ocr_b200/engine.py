@@ -388,8 +388,7 @@ class Engine:
             # kernel of the chain; the embed kernel zeroes them and, like the argmax kernel, keeps its grid dependency.
             deps = bool(pl.get("deps"))
             tiles = lambda n: -(-n // 128)
-            n_sig = (8 * tiles(qkv_n) * pl["qkv"], 8 * B * nkv, 8 * tiles(H) * pl["o"], (H // 256) * B, 8 * tiles(2 * I), 8 * tiles(H) * pl["down"],
-                     (H // 256) * B)
+            n_sig = (tiles(qkv_n) * pl["qkv"], B * nkv, tiles(H) * pl["o"], B, tiles(2 * I), tiles(H) * pl["down"], B)      # signals per launch
             ctr = st["counters"]
 
             def arm(li: int, k: int) -> None:

@@ -272,8 +272,8 @@ DOTS_API int dots_decode_gemm_max_clusters(int batch, int* out);
  * _swiglu / _head, dots_attn_decode_fused with n_splits == 1, dots_decode_residual_rmsnorm), counters in device memory instead:
  *   wait_counter   (u32, or NULL = keep the grid dependency): the launch's first dependent access waits until the counter has reached
  *                  wait_target;
- *   signal_counter (u32, or NULL): every producer warp of the launch adds 1 after its last global store.  Signals per launch:
- *                  GEMMs 8 x ceil(N / 128) x splits; attention 8 x batch x n_kv_heads; residual_rmsnorm ceil(H / 256) x batch.
+ *   signal_counter (u32, or NULL): every CTA of the launch (every output tile for the GEMMs) adds 1 after its last global store.
+ *                  Signals per launch: GEMMs ceil(N / 128) x splits; attention batch x n_kv_heads; residual_rmsnorm batch.
  * The counters of a step must be zero before its first consumer starts: pass them to dots_decode_embed_rmsnorm (counters, n_counters),
  * the first kernel of the step, which zeroes them before it releases its dependents; that kernel and dots_argmax_advance keep their grid
  * dependency, so consecutive steps never overlap.  A launch with a wait_counter never executes griddepcontrol.wait: every buffer it

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ctx", type=int, default=1881)
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0)
+    ap.add_argument("--deps", type=int, default=1, help="1: dependency counters between the kernels (default), 0: grid dependencies")
     ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay of the step (default: eager launches with PDL)")
     ap.add_argument("--show-layers", dest="show", type=int, default=2, help="print the kernels of this many layers (from layer 3 on)")
     a = ap.parse_args()
@@ -35,6 +36,7 @@ def main():
     eng = Engine(cfg, weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev), dev)
     eng.decode_mode = a.mode
     eng.attn_splits = a.attn_splits
+    eng.decode_deps = bool(a.deps)
     B = a.batch
     ctx_max = (a.ctx + 16 + 63) // 64 * 64
     kc, vc = eng._alloc_cache(B, ctx_max)
@@ -44,18 +46,21 @@ def main():
     st["last"].random_(0, 150000)
     for _ in range(3):
         eng._decode_step(st)
-    g = ops.capture(lambda: eng._decode_step(st)) if a.graph else None
+    side = torch.cuda.Stream(device=dev)           # stream capture is not allowed on the legacy default stream
+    torch.cuda.synchronize()
     cap = 400000
     buf = torch.zeros(2 + 3 * cap, device=dev, dtype=torch.int64)
     buf[1] = cap
     torch.cuda.synchronize()
     ops.debug_set_trace(buf)
-    if g is not None:
-        # the trace pointer is a kernel parameter: re-capture with it armed
-        g = ops.capture(lambda: eng._decode_step(st))
-        g.launch(); torch.cuda.synchronize()
-        buf[0] = 0
-        g.launch()
+    if a.graph:
+        # the trace pointer is a kernel parameter: capture with it armed
+        with torch.cuda.stream(side):
+            g = ops.capture(lambda: eng._decode_step(st))
+            g.launch(); torch.cuda.synchronize()
+            buf[0] = 0
+            torch.cuda.synchronize()
+            g.launch()
     else:
         eng._decode_step(st)
     torch.cuda.synchronize()

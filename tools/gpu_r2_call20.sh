@@ -11,7 +11,19 @@ except Exception as e:
     print("$name failed", e, open("gpurun_out/ablate_r2q_$name.err").read()[-900:])
 PY
 }
-abl deps --mode tiled --quick --deps 1
-abl nodeps --mode tiled --quick --deps 0
-timeout 200 python tools/decode_timeline.py --mode tiled > gpurun_out/timeline_r2q_deps.txt 2>&1; head -12 gpurun_out/timeline_r2q_deps.txt | cut -c1-200
-timeout 200 python tools/decode_timeline.py --mode tiled --graph > gpurun_out/timeline_r2q_deps_graph.txt 2>&1; head -12 gpurun_out/timeline_r2q_deps_graph.txt | cut -c1-200
+abl deps2 --mode tiled --quick --deps 1
+abl nodeps2 --mode tiled --quick --deps 0
+timeout 200 python tools/decode_timeline.py --mode tiled > gpurun_out/timeline_r2r_deps.txt 2>&1; head -12 gpurun_out/timeline_r2r_deps.txt | cut -c1-200
+timeout 200 python tools/decode_timeline.py --mode tiled --graph > gpurun_out/timeline_r2r_deps_graph.txt 2>&1; head -12 gpurun_out/timeline_r2r_deps_graph.txt | cut -c1-200
+python - <<'PY'
+import torch
+from dots_ocr_b200 import config, weights
+from dots_ocr_b200.engine import Engine
+import subprocess, sys
+PY
+DOTS_NO_DEPS=1 timeout 200 python - <<'PY' > gpurun_out/timeline_r2r_nodeps_graph.txt 2>&1
+import sys, runpy
+sys.argv = ["tools/decode_timeline.py", "--mode", "tiled", "--graph", "--deps", "0"]
+runpy.run_path("tools/decode_timeline.py", run_name="__main__")
+PY
+head -10 gpurun_out/timeline_r2r_nodeps_graph.txt | cut -c1-200
