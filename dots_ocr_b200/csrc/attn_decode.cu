@@ -71,7 +71,6 @@ struct DecParams {
     int out_tile_rows;        // > 0: `out` is written in the k-block-tiled activation layout with this many rows per tile
     int cluster_merge;        // 1: the n_splits CTAs of a (sequence, kv head) are one cluster and merge through DSMEM
     int fault;                // test-only fault injection (dots_debug_set_fault): 1 = key tile 0, 2 = every other key tile loses its P*V term
-    DepSpec dep;              // dependency counters of the decode step (ptx.cuh); honoured only on the fused path with n_splits == 1
     const bf16* qkv_bias;
     const int* pos;
     const float* inv_freq;
@@ -159,7 +158,7 @@ attn_decode_kernel(const DecParams p) {
             for (; i < early && i < DEC_STAGES; ++i) issue(i);          // ring-full of immutable tiles ahead of the wait
         }
         __syncwarp();
-        if (p.dep.wait_ctr == nullptr) pdl_wait();     // with counters: every tile is immutable or completed by this CTA's own consumer warps
+        pdl_wait();
         if (lane == 0) trace_point(p.trace, 20, 1);
         if (fused && holds_new) {
             // the appended k/v row is produced by the consumer warps of this CTA: wait until they published it
@@ -204,12 +203,7 @@ attn_decode_kernel(const DecParams p) {
             }
         }
     }
-    if (p.dep.wait_ctr != nullptr) {
-        if (tid == 0) dep_wait(p.dep.wait_ctr, p.dep.wait_target);         // the q|k|v GEMM's partials are complete
-        asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");  // one poller per CTA, the consumer warps follow it
-    } else {
-        pdl_wait();
-    }
+    pdl_wait();
 
     // Q tile: rows 0..G-1 = the group's q heads, rows G..15 zero
     if (!fused) {
@@ -441,11 +435,6 @@ attn_decode_kernel(const DecParams p) {
         for (int r = 0; r < 8; ++r)
             if (r % PARTS == part && r < p.group)
                 p.out[dec_out_off(p, b, (kvh * p.group + r) * DEC_D + c)] = __float2bfloat16_rn(lv[r] > 0.f ? accv[r] / lv[r] : 0.f);
-        if (p.dep.signal_ctr != nullptr) {                                                // one signal per CTA
-            dep_publish();
-            asm volatile("bar.sync 1, %0;" ::"n"(DEC_WARPS * 32) : "memory");
-            if (tid == 0) dep_signal(p.dep.signal_ctr);
-        }
     } else if (p.cluster_merge) {
         // ---- on-chip merge across the cluster: peers write (O, m, l) into the leader's shared memory, the leader combines
         //      in split order (same arithmetic as attn_decode_combine_kernel) ----
@@ -582,12 +571,6 @@ extern "C" int dots_attn_decode_fused(const float* qkv_partial, int qkv_splits, 
     p.out = (bf16*)out; p.part_o = part_o; p.part_ml = part_ml; p.ctx_max = ctx_max;
     p.qkv_partial = qkv_partial; p.qkv_splits = qkv_splits; p.qkv_bias = (const bf16*)qkv_bias; p.pos = pos; p.inv_freq = inv_freq;
     p.kc_w = (bf16*)k_cache; p.vc_w = (bf16*)v_cache;
-    {
-        const HostDeps d = take_deps();
-        DOTS_REQUIRE((d.wait_ctr == nullptr && d.signal_ctr == nullptr) || n_splits == 1,
-                     "dots_attn_decode_fused: dependency counters need n_splits == 1 (got %d)", n_splits);
-        p.dep.wait_ctr = d.wait_ctr; p.dep.wait_target = d.wait_target; p.dep.signal_ctr = d.signal_ctr;
-    }
     return launch_attn_decode(p, batch, n_q_heads, n_kv_heads, head_dim, n_splits, softmax_scale, stream, "dots_attn_decode_fused");
 }
 

@@ -17,13 +17,6 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static thread_local HostDeps g_next_deps = {nullptr, 0u, nullptr};
-HostDeps take_deps() {
-    HostDeps d = g_next_deps;
-    g_next_deps = HostDeps{nullptr, 0u, nullptr};
-    return d;
-}
-
 int num_sms() {
     static int cache[64] = {0};          // per device: one process may drive several GPUs
     int dev = 0;
@@ -153,10 +146,5 @@ extern "C" int dots_graph_launch(void* graph_exec, void* stream) {
 }
 extern "C" int dots_graph_destroy(void* graph_exec) {
     if (graph_exec) DOTS_CHECK_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
-    return 0;
-}
-
-extern "C" int dots_decode_deps(void* wait_counter, unsigned int wait_target, void* signal_counter) {
-    dots::g_next_deps = dots::HostDeps{reinterpret_cast<unsigned*>(wait_counter), wait_target, reinterpret_cast<unsigned*>(signal_counter)};
     return 0;
 }

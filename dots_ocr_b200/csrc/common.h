@@ -81,14 +81,6 @@ inline cudaError_t launch_ex_cluster(void (*kern)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-// Dependency counters of the next decode-step launch (dots_decode_deps): one-shot, per host thread; take_deps() returns and clears.
-struct HostDeps {
-    unsigned* wait_ctr;
-    unsigned wait_target;
-    unsigned* signal_ctr;
-};
-HostDeps take_deps();
-
 // 2-D bf16 row-major tensor [rows, cols] with row pitch ld (elements) -> TMA map with a
 // {64 x box_rows} box and 128-byte swizzle.  Returns 0 on success.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,

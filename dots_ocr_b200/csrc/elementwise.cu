@@ -484,15 +484,10 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
                                                                    bf16* __restrict__ normed, int B, int H, float eps,
                                                                    unsigned* __restrict__ counters, int n_counters, int tile_rows) {
     pdl_wait();
-    // first kernel of a decode step: re-arm this step's counters (rendezvous counters of dots_decode_gemm_resnorm, dependency counters
-    // of dots_decode_deps).  The previous step has completed (the wait above), and nothing of this step may start before the zeros are
-    // visible: the dependents are released only afterwards.
-    if (blockIdx.x == 0 && n_counters > 0) {
-        for (int i = threadIdx.x; i < n_counters; i += blockDim.x) counters[i] = 0u;
-        __threadfence();
-        __syncthreads();
-    }
     pdl_launch_dependents();
+    // first kernel of a decode step: re-arm the rendezvous counters of this step's dots_decode_gemm_resnorm launches
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n_counters; i += blockDim.x) counters[i] = 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
     if (b >= B) return;
@@ -537,16 +532,10 @@ __global__ void __launch_bounds__(256) decode_embed_rmsnorm_kernel(const long lo
 __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const float* __restrict__ partial, int splits,
                                                                       bf16* __restrict__ resid, const bf16* __restrict__ w,
                                                                       bf16* __restrict__ normed, int B, int H, float eps, int tile_rows,
-                                                                      unsigned long long* trace, const DepSpec dep) {
+                                                                      unsigned long long* trace) {
     if (threadIdx.x == 0) trace_point(trace, 30, 0);
-    if (dep.wait_ctr != nullptr) {
-        if (threadIdx.x == 0) dep_wait(dep.wait_ctr, dep.wait_target);            // the split-K partials are complete
-        __syncthreads();
-    } else {
-        pdl_wait();
-    }
-    // (releasing the dependents ahead of the wait was measured: the run-ahead kernels cost more than their earlier prefetch gains)
-    pdl_launch_dependents();
+    pdl_wait();
+    pdl_launch_dependents();        // (releasing the dependents ahead of the wait was measured: 1.845 against 1.832 ms per step)
     if (threadIdx.x == 0) trace_point(trace, 30, 1);
     __shared__ float s_part[8];
     const int b = blockIdx.x;
@@ -586,11 +575,6 @@ __global__ void __launch_bounds__(256) decode_residual_rmsnorm_kernel(const floa
         for (int j = 0; j < 8; ++j) f[j] = bf16_round(x[j] * r) * g[j];
         bf16* dst = tile_rows > 0 ? normed + tiled_row_off(b, c * 8, tile_rows) : normed + (long long)b * H + c * 8;
         *reinterpret_cast<uint4*>(dst) = pack8(f);
-    }
-    if (dep.signal_ctr != nullptr) {                                                       // one signal per CTA
-        dep_publish();
-        __syncthreads();
-        if (threadIdx.x == 0) dep_signal(dep.signal_ctr);
     }
     if (threadIdx.x == 0) trace_point(trace, 30, 4);
 }
@@ -805,9 +789,7 @@ extern "C" int dots_decode_residual_rmsnorm(const float* partial, int splits, vo
     DOTS_REQUIRE(batch > 0 && splits > 0 && H % 8 == 0 && H <= NORM_MAX_CHUNKS * 256, "dots_decode_residual_rmsnorm: bad shape");
     DOTS_REQUIRE(tile_rows == 0 || (tile_rows % 8 == 0 && batch <= tile_rows && H % 64 == 0), "dots_decode_residual_rmsnorm: bad tile_rows %d", tile_rows);
     const int threads = ((H / 8) + 31) / 32 * 32;
-    const HostDeps hd = take_deps();
-    const DepSpec dep{hd.wait_ctr, hd.wait_target, hd.signal_ctr};
-    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps, tile_rows, g_trace, dep));
+    DOTS_CHECK_CUDA(launch_ex(decode_residual_rmsnorm_kernel, dim3(batch), dim3(threads), (size_t)(0), ST(stream), true, partial, splits, (bf16*)resid, (const bf16*)w, (bf16*)normed, batch, H, eps, tile_rows, g_trace));
     return 0;
 }
 

@@ -41,7 +41,6 @@ struct GemmParams {
     int rope_cols;
     unsigned long long* trace;     // timeline instrumentation (nullptr unless armed)
     int stages;                    // ring depth of this launch (0: the template's STAGES)
-    DepSpec dep;                   // decode step: dependency counters instead of the grid dependency (ptx.cuh); all null otherwise
 };
 
 constexpr bool epi_is_swap_ab(int epi) { return epi == DOTS_EPI_F32_PARTIAL_T || epi == DOTS_EPI_BF16_T || epi == DOTS_EPI_SWIGLU_T; }
@@ -406,8 +405,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     else load_a(pre, kb, m_blk);
                 }
             }
-            if (p.dep.wait_ctr != nullptr) dep_wait(p.dep.wait_ctr, p.dep.wait_target);    // the activation operand is complete
-            else pdl_wait();
+            pdl_wait();
             trace_point(p.trace, TRACE_KID, 1);
             int issued = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -476,9 +474,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // residual / bias reads and all output writes follow the dependency.  With dependency counters the accumulator itself is
-        // downstream of the producer warp's counter wait, and the output buffer's previous readers signalled before that count was reached.
-        if (p.dep.wait_ctr == nullptr) pdl_wait();
+        pdl_wait();                                          // residual / bias reads and all output writes follow the dependency
         const int wq = warp & 3;                             // TMEM lane quarter this warp may read
         const int eg = (warp - 4) >> 2;                      // epilogue group: which half of the tile's columns
         int acc = 0;
@@ -492,11 +488,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
 
             gemm_epilogue_tile<BLOCK_N, EPI>(p, row, m_blk, n_blk, split, t_row, eg, wq, lane, xch);
-            if (p.dep.signal_ctr != nullptr) {                                            // one signal per tile
-                dep_publish();
-                asm volatile("bar.sync 3, %0;" ::"n"(128 * EPI_GROUPS) : "memory");      // all epilogue warps have stored and fenced
-                if (threadIdx.x == 128) dep_signal(p.dep.signal_ctr);
-            }
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -908,7 +899,6 @@ extern "C" int dots_decode_gemm_swiglu(const void* Xt, const void* Wt, void* act
                  "dots_decode_gemm_swiglu: bad arguments batch=%d 2I=%d K=%d", batch, two_i, K);
     DOTS_REQUIRE((two_i / 2) % 64 == 0, "dots_decode_gemm_swiglu: I must be a multiple of 64 (tiled output)");
     GemmParams p{};
-    { const HostDeps d = take_deps(); p.dep.wait_ctr = d.wait_ctr; p.dep.wait_target = d.wait_target; p.dep.signal_ctr = d.signal_ctr; }
     p.static_is_b = 0;
     p.M = two_i; p.N = batch; p.K = K;
     p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
@@ -934,7 +924,6 @@ extern "C" int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_ro
     const int bn = batch <= 32 ? 32 : 64;
     DOTS_REQUIRE(x_tile_rows == 0 || x_tile_rows == bn, "dots_decode_gemm_head: x_tile_rows must be 0 or %d for batch %d", bn, batch);
     GemmParams p{};
-    { const HostDeps d = take_deps(); p.dep.wait_ctr = d.wait_ctr; p.dep.wait_target = d.wait_target; p.dep.signal_ctr = d.signal_ctr; }
     p.static_is_b = 0;
     p.M = N; p.N = batch; p.K = K;
     p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
@@ -960,7 +949,6 @@ extern "C" int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_ro
 extern "C" int dots_decode_gemm_partial(const void* Xt, const void* Wt, float* partial, int batch, int N, int K, int splits, void* stream) {
     DOTS_REQUIRE(Xt && Wt && partial && batch > 0 && batch <= 64 && N > 0 && K > 0, "dots_decode_gemm_partial: bad arguments batch=%d N=%d K=%d", batch, N, K);
     GemmParams p{};
-    { const HostDeps d = take_deps(); p.dep.wait_ctr = d.wait_ctr; p.dep.wait_target = d.wait_target; p.dep.signal_ctr = d.signal_ctr; }
     p.static_is_b = 0;
     p.M = N; p.N = batch; p.K = K;
     p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;

@@ -272,41 +272,6 @@ __device__ __forceinline__ uint64_t fmul_f32x2(uint64_t a, uint64_t b) {
     return d;
 }
 
-// ---------------------------------------------------------------- dependency counters between the kernels of a decode step
-// A dependent kernel boundary (griddepcontrol.wait) releases the successor ~1.2-1.9 us after the predecessor's last CTA has left:
-// the whole grid must have completed and flushed.  The decode step pays that seven times per layer.  With a counter, every
-// producer warp publishes "my stores are done" (device-scope fence, then one atomic), and the consumer's first dependent access
-// spins on the count (an L2 round trip).  The counters of a step are zeroed by its first kernel (decode_embed_rmsnorm) before that
-// kernel lets its dependents start, and the step's last kernels keep the grid dependency, so steps never overlap.
-struct DepSpec {
-    unsigned* wait_ctr;      // nullptr: griddepcontrol.wait
-    unsigned wait_target;
-    unsigned* signal_ctr;    // nullptr: no signal
-};
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// wait until `target` producer warps have signalled; the caller's later generic-proxy AND async-proxy (bulk copy) reads see their data
-__device__ __forceinline__ void dep_wait(const unsigned* ctr, unsigned target) {
-    unsigned spins = 0;
-    while (ld_acquire_gpu_u32(ctr) < target) {
-        __nanosleep(40);
-        if (++spins > (1u << 23)) { printf("dots: dependency counter watchdog (block %d, have %u of %u)\n", (int)blockIdx.x, ld_acquire_gpu_u32(ctr), target); __trap(); }
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");
-}
-// Signalling is per CTA (per tile for the persistent GEMMs): every storing thread calls dep_publish() after its last global store, the
-// CTA's storing threads meet at a barrier of the caller's choice, then ONE thread calls dep_signal().  (Per-warp signals and per-warp
-// polling were measured first: ~1000 same-address atomics plus ~1000 spinning warps per hop saturate the L2 slice that owns the
-// counter, and the step got 0.4 ms slower instead of faster.)
-__device__ __forceinline__ void dep_publish() {
-    asm volatile("fence.proxy.async;" ::: "memory");     // the consumer may read these generic-proxy stores through bulk copies
-    __threadfence();
-}
-__device__ __forceinline__ void dep_signal(unsigned* ctr) { atomicAdd(ctr, 1u); }
-
 // ---------------------------------------------------------------- timeline instrumentation (tools/decode_timeline.py)
 // One record = 3 x u64: (kernel id << 48 | point << 40 | linear CTA index), %globaltimer [ns], clock64.  `buf` is nullptr unless
 // dots_debug_set_trace() armed it: the cost in normal operation is one predictable branch per call site.

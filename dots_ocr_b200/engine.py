@@ -176,7 +176,6 @@ class Engine:
         #   "perop"  7 kernels per layer over row-major operands and tensor-map copies; the only mode for batches of 65..256
         self.decode_mode = "tiled"
         self.attn_splits = 0            # 0: planned from the batch size; n: force n key splits in decode attention (tuning runs)
-        self.decode_deps = True         # tiled mode, one attention CTA per (sequence, kv head): dependency counters between the kernels of a step
         self.decode_sms = 0             # 0: plan the decode step for the whole device; n: for an SM partition of n SMs (pipeline.py)
         self._fused_ok: Dict[int, bool] = {}
         self._dec_cache: Optional[dict] = None
@@ -353,7 +352,6 @@ class Engine:
             gu=ops.pick_splits(tiles(2 * I), kb(H), sms),
             down=ops.pick_splits(tiles(H), kb(I), sms),
             attn=attn,
-            deps=bool(self.decode_deps and mode == "tiled" and attn == 1),
         )
 
     def _decode_step(self, st: dict):
@@ -383,44 +381,18 @@ class Engine:
             ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
         elif pl["mode"] == "tiled":
             R = st["tile_rows"]
-            # Dependency counters instead of grid dependencies between the kernels of the step (ops.decode_deps): counter 7 * layer + k
-            # is signalled by kernel k of that layer (q|k|v, attention, o, finalize, gate|up, down, finalize) and awaited by the next
-            # kernel of the chain; the embed kernel zeroes them and, like the argmax kernel, keeps its grid dependency.
-            deps = bool(pl.get("deps"))
-            tiles = lambda n: -(-n // 128)
-            n_sig = (tiles(qkv_n) * pl["qkv"], B * nkv, tiles(H) * pl["o"], B, tiles(2 * I), tiles(H) * pl["down"], B)      # signals per launch
-            ctr = st["counters"]
-
-            def arm(li: int, k: int) -> None:
-                """kernel k of layer li (k == 0 of layer n_layers: lm_head): wait for its predecessor, signal its own counter"""
-                if not deps:
-                    return
-                i = 7 * li + k
-                wait = ctr[i - 1:i] if i > 0 else None
-                sig = ctr[i:i + 1] if li < n_layers else None
-                ops.decode_deps(wait, n_sig[(k - 1) % 7], sig)
-
-            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps,
-                                     counters=ctr if deps else None, tile_rows=R)
+            ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
             for li, L in enumerate(self.t_layers):
                 nxt = self.t_layers[li + 1]["ln1"] if li + 1 < n_layers else self.final_norm
-                arm(li, 0)
                 ops.decode_gemm_partial(st["normed_t"], L["qkv_w_t"], st["partial"], B, qkv_n, H, pl["qkv"])
-                arm(li, 1)
                 ops.attn_decode_fused(st["partial"], pl["qkv"], L["qkv_b"], st["pos"], self.t_inv_freq, st["kc"][li], st["vc"][li],
                                       st["ctx_len"], st["attn_t"], nq, nkv, st["ctx_max"], pl["attn"], scale, st["part_o"], st["part_ml"],
                                       out_tile_rows=R)
-                arm(li, 2)
                 ops.decode_gemm_partial(st["attn_t"], L["o_t"], st["partial"], B, H, nq * hd, pl["o"])
-                arm(li, 3)
                 ops.decode_residual_rmsnorm(st["partial"], pl["o"], st["resid"], L["ln2"], st["normed_t"], t.rms_norm_eps, tile_rows=R)
-                arm(li, 4)
                 ops.decode_gemm_swiglu(st["normed_t"], L["gu_t"], st["act_t"], B, H)
-                arm(li, 5)
                 ops.decode_gemm_partial(st["act_t"], L["down_t"], st["partial"], B, H, I, pl["down"])
-                arm(li, 6)
                 ops.decode_residual_rmsnorm(st["partial"], pl["down"], st["resid"], nxt, st["normed_t"], t.rms_norm_eps, tile_rows=R)
-            arm(n_layers, 0)
             ops.decode_gemm_head(st["normed_t"], self.lm_head_t, st["logits"], t.vocab_size, H, tiled=True)
         else:
             ops.decode_embed_rmsnorm(st["last"], self.embed, self.t_layers[0]["ln1"], st["resid"], st["normed"], t.rms_norm_eps)
@@ -470,7 +442,7 @@ class Engine:
             tiled = lambda k: torch.zeros(-(-k // 64) * R * 64, device=dev, dtype=torch.bfloat16)
             st["normed_t"], st["attn_t"], st["act_t"] = tiled(H), tiled(t.num_attention_heads * t.head_dim), tiled(t.intermediate_size)
         st["stats"] = torch.zeros((2, -(-H // 128) * 64), device=dev, dtype=torch.float32)
-        st["counters"] = torch.zeros(7 * t.num_hidden_layers + 1, device=dev, dtype=torch.int32)
+        st["counters"] = torch.zeros(2 * t.num_hidden_layers, device=dev, dtype=torch.int32)
         return st
 
     def decode_weight_bytes(self) -> int:
@@ -540,7 +512,7 @@ class Engine:
         # KV cache, decode workspaces and the captured decode graph are kept from call to call when the shape key repeats
         # (a serving loop and the benchmark call generate with the same batch geometry over and over)
         stops_key = tuple(stop_list(eos_token_id)[: ops.MAX_STOP_IDS])
-        key = (B, ctx_max, N, stops_key, int(pad_token_id), self.decode_mode, self.attn_splits, ops.DECODE_CLUSTER, int(self.decode_sms), bool(self.decode_deps))
+        key = (B, ctx_max, N, stops_key, int(pad_token_id), self.decode_mode, self.attn_splits, ops.DECODE_CLUSTER, int(self.decode_sms))
         ent = self._dec_cache if (self._dec_cache is not None and self._dec_cache["key"] == key and forced_ids is None) else None
         if ent is None:
             self._dec_cache = None                      # release the previous geometry's buffers before allocating new ones

@@ -376,15 +376,6 @@ def decode_embed_rmsnorm(ids, table, w, resid, normed, eps, counters=None, tile_
     _lib.check(rc, "dots_decode_embed_rmsnorm")
 
 
-def decode_deps(wait: Optional[torch.Tensor], target: int, signal: Optional[torch.Tensor]) -> None:
-    """Arm dependency counters (one-element int32 CUDA views) for the NEXT decode launch of this thread: it waits until ``wait`` has
-    reached ``target`` instead of taking the grid dependency, and every producer warp adds 1 to ``signal`` after its last store
-    (include/dots_ocr_b200.h "dependency counters").  Either may be None."""
-    for t in (wait, signal):
-        assert t is None or (t.is_cuda and t.dtype == torch.int32 and t.numel() >= 1)
-    _lib.check(_lib.load().dots_decode_deps(_p(wait), C.c_uint(int(target)), _p(signal)), "dots_decode_deps")
-
-
 def decode_tile_rows(batch: int) -> int:
     """Rows per tile of the k-block-tiled activation buffers of a decode step with this batch size."""
     assert 0 < batch <= 64

@@ -266,20 +266,6 @@ DOTS_API int dots_decode_gemm_head(const void* X, long long ldx, int x_tile_rows
 /* Number of 8-CTA clusters of dots_decode_gemm_resnorm the current device keeps resident at once. */
 DOTS_API int dots_decode_gemm_max_clusters(int batch, int* out);
 
-/* ---- dependency counters between the kernels of one decode step -------------------------------
- * A grid dependency releases the next kernel 1.2-1.9 us after the previous kernel's last CTA has left; the decode step pays that seven
- * times per layer.  dots_decode_deps() arms, for the NEXT decode launch of the calling host thread only (dots_decode_gemm_partial /
- * _swiglu / _head, dots_attn_decode_fused with n_splits == 1, dots_decode_residual_rmsnorm), counters in device memory instead:
- *   wait_counter   (u32, or NULL = keep the grid dependency): the launch's first dependent access waits until the counter has reached
- *                  wait_target;
- *   signal_counter (u32, or NULL): every CTA of the launch (every output tile for the GEMMs) adds 1 after its last global store.
- *                  Signals per launch: GEMMs ceil(N / 128) x splits; attention batch x n_kv_heads; residual_rmsnorm batch.
- * The counters of a step must be zero before its first consumer starts: pass them to dots_decode_embed_rmsnorm (counters, n_counters),
- * the first kernel of the step, which zeroes them before it releases its dependents; that kernel and dots_argmax_advance keep their grid
- * dependency, so consecutive steps never overlap.  A launch with a wait_counter never executes griddepcontrol.wait: every buffer it
- * writes must have had its last readers upstream of the counter it waits on (true for the step as dots_ocr_b200/engine.py issues it). */
-DOTS_API int dots_decode_deps(void* wait_counter, unsigned int wait_target, void* signal_counter);
-
 /* ---- SM partitions (two phases of the page pipeline side by side on one GPU) -------------------
  * dots_partition_create splits the current device's SMs into a first group of `sms_first` SMs (a multiple of 8; it keeps the
  * thread-block-cluster guarantees, so the CTA-pair prefill GEMMs go there) and the rest, as two CUDA green contexts, and returns

@@ -232,45 +232,3 @@ def test_engine_decode_modes_agree():
                           return_logits=True).logits.float().cpu()
         sd = float(res["perop"][1].std())
         assert float((lf - res["perop"][1]).abs().max()) / sd < 6e-2
-
-
-def test_dependency_counters_change_nothing_but_the_schedule():
-    """Engine.decode_deps (tiled mode, one attention CTA per (sequence, kv head)): the kernels of a step wait on per-kernel completion
-    counters instead of grid dependencies.  Same arithmetic in the same order: greedy ids and teacher-forced logits are bit-identical
-    with the counters on and off, under graph replay (where the kernels really overlap) and eager stepping, for ragged prompts."""
-    from dots_ocr_b200 import config, weights
-    from dots_ocr_b200.engine import Engine
-    cfg = config.tiny()
-    g = torch.Generator().manual_seed(9)
-    grids = [(1, 8, 8), (1, 4, 12), (1, 8, 12), (1, 8, 8), (1, 4, 8)]
-    pvs, rows = [], []
-    for (_, h, w) in grids:
-        pvs.append(torch.randn(h * w, cfg.vision.patch_dim, generator=g))
-        rows.append(torch.cat([torch.randint(0, 2000, (5,), generator=g), torch.full((h * w // 4,), cfg.image_token_id),
-                               torch.randint(0, 2000, (int(torch.randint(3, 12, (1,), generator=g)),), generator=g)]))
-    T = max(r.numel() for r in rows)
-    n = len(rows)
-    ids = torch.zeros((n, T), dtype=torch.long)
-    mask = torch.zeros((n, T), dtype=torch.long)
-    for i, r in enumerate(rows):
-        ids[i, T - r.numel():] = r
-        mask[i, T - r.numel():] = 1
-    pv, grid = torch.cat(pvs).to(DEV), torch.tensor(grids)
-    eng = Engine(cfg, weights.make_synthetic_checkpoint(cfg, 0, "random"), DEV)
-    eng.attn_splits = 1                     # the configuration the counters are defined for (the benchmark's plan)
-    res = {}
-    for deps in (False, True, False, True):
-        eng.decode_deps = deps
-        assert eng._decode_plan(n)["deps"] == deps
-        a = eng.generate(ids, attention_mask=mask, pixel_values=pv, image_grid_thw=grid, max_new_tokens=70)
-        b = eng.generate(ids, attention_mask=mask, pixel_values=pv, image_grid_thw=grid, max_new_tokens=70, use_graph=False, return_logits=True)
-        assert torch.equal(a.sequences, b.sequences), deps
-        if deps in res:
-            assert torch.equal(res[deps][0], a.sequences.cpu()) and torch.equal(res[deps][1], b.logits.float().cpu())
-        res[deps] = (a.sequences.cpu(), b.logits.float().cpu())
-    assert torch.equal(res[True][0], res[False][0])
-    assert torch.equal(res[True][1], res[False][1])
-    # with key splits (flash decoding) the plan falls back to grid dependencies
-    eng.attn_splits = 0
-    eng.decode_deps = True
-    assert eng._decode_plan(n)["deps"] == (eng._decode_plan(n)["attn"] == 1)

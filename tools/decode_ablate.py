@@ -28,7 +28,6 @@ def main():
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0, help="override the flash-decoding split count of the plan")
     ap.add_argument("--no-cluster", action="store_true", help="combine kernel instead of the cluster merge for 2..4 attention splits")
     ap.add_argument("--quick", action="store_true", help="only the full step and the attention ablation")
-    ap.add_argument("--deps", type=int, default=1, help="1: dependency counters between the kernels of the step (default), 0: grid dependencies")
     ap.add_argument("--stages", default=None, help="ring depths partial,swiglu,head of the decode GEMMs (e.g. 4,5,4)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -36,7 +35,6 @@ def main():
     ck = weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev)
     eng = Engine(cfg, ck, dev)
     eng.decode_mode = args.mode
-    eng.decode_deps = bool(args.deps)
     del ck
     if args.no_cluster:
         ops.set_decode_cluster(False)
@@ -55,8 +53,6 @@ def main():
 
     def run(stub=()):
         """stub: iterable of (op name, weight shape or None)."""
-        # a stubbed-out kernel never signals its counter: the ablation runs use grid dependencies (compare them with full_griddep_ms)
-        eng.decode_deps = bool(args.deps) and not stub
         st = eng._new_decode_state(B, lens, kc, vc, ctx_max, args.steps + 2)
         st["last"].random_(0, 150000)
         for n, f in real.items():
@@ -91,15 +87,8 @@ def main():
 
     full = run()
     pl = eng._decode_plan(B)
-    full_deps = None
-    if args.deps:
-        full_deps = full
-        eng.decode_deps = False
-        args_deps, args.deps = args.deps, 0
-        full = run()                      # the reference for the stubbed runs below
-        args.deps = args_deps
     L0 = eng.t_layers[0]
-    res = {"full_ms": round(full_deps if full_deps is not None else full, 4), "full_griddep_ms": round(full, 4), "plan": {k: v for k, v in pl.items()}}
+    res = {"full_ms": round(full, 4), "plan": {k: v for k, v in pl.items()}}
     if pl["mode"] == "fused":
         cases = [("attention(+rope, append)", [("attn_decode_qkv", None)]),
                  ("qkv gemm (cluster)", [("decode_gemm_qkv", None)]),
@@ -131,7 +120,6 @@ def main():
         ms = run(stub)
         res[name] = {"without_ms": round(ms, 4), "cost_ms": round(full - ms, 4), "per_layer_us": round((full - ms) * 1e3 / t.num_hidden_layers, 2)}
     res["full_again_ms"] = round(run(), 4)
-    full = full_deps if full_deps is not None else full
     w_bytes = eng.decode_weight_bytes()
     kv_bytes = 2 * t.num_hidden_layers * t.num_key_value_heads * t.head_dim * 2 * args.ctx * B
     res["roofline_ms_at_6485GBs"] = round((w_bytes + kv_bytes) / 6485.2e9 * 1e3, 4)

@@ -27,7 +27,6 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ctx", type=int, default=1881)
     ap.add_argument("--attn-splits", dest="attn_splits", type=int, default=0)
-    ap.add_argument("--deps", type=int, default=1, help="1: dependency counters between the kernels (default), 0: grid dependencies")
     ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay of the step (default: eager launches with PDL)")
     ap.add_argument("--show-layers", dest="show", type=int, default=2, help="print the kernels of this many layers (from layer 3 on)")
     a = ap.parse_args()
@@ -36,7 +35,6 @@ def main():
     eng = Engine(cfg, weights.make_synthetic_checkpoint(cfg, 0, "random", device=dev), dev)
     eng.decode_mode = a.mode
     eng.attn_splits = a.attn_splits
-    eng.decode_deps = bool(a.deps)
     B = a.batch
     ctx_max = (a.ctx + 16 + 63) // 64 * 64
     kc, vc = eng._alloc_cache(B, ctx_max)
