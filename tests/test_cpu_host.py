@@ -621,3 +621,23 @@ def test_grounding_prompt_bbox_uses_the_reference_rounding():
     want = pre_process_bboxes(origin, [[85, 85, 120, 130]], input_width=1092, input_height=1092, min_pixels=3136, max_pixels=11289600)[0]
     assert got == dict_promptmode_to_prompt["prompt_grounding_ocr"] + str(want)
     assert want[0] == 455 and int(85 * (1092 / 204)) == 454
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_ncu_capture():
+    """bench.py fills `roofline.traffic` from profiles/decode_traffic_*.json (the ncu `dram__bytes` of one decode step) and ties its ids
+    to the parity test through tests/golden/bench_ids_checksum.json: both files must be present and well formed."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    tr = bench._decode_traffic()
+    assert tr is not None and tr["file"].startswith("decode_traffic_") and tr["steps"] >= 1
+    # one step moves at least the decoder weights + lm_head (3.09 GB) and not absurdly more than the algorithmic 6.54 GB at B=64, ctx 1.9k
+    assert 3.0e9 < tr["dram_bytes_per_step"] < 2 * 6.54e9
+    with open(os.path.join(root, "tests", "golden", "bench_ids_checksum.json")) as f:
+        g = json.load(f)
+    assert isinstance(g["b64_n512_p1024_rank0"], str) and len(g["b64_n512_p1024_rank0"]) == 16
+    ids = __import__("torch").arange(12).view(3, 4)
+    assert bench.ids_checksum(ids) == bench.ids_checksum(ids.clone()) != bench.ids_checksum(ids + 1)
